@@ -1,0 +1,48 @@
+// elo_common.cu -- error reporting and device-property cache for libelo_b200.so.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/elo_b200.h"
+#include "elo_common.cuh"
+
+namespace elo {
+
+static thread_local char g_error[512] = "";
+
+int set_error(int code, const char* msg)
+{
+    snprintf(g_error, sizeof(g_error), "%s", msg);
+    return code;
+}
+
+int set_cuda_error(cudaError_t err, const char* where)
+{
+    snprintf(g_error, sizeof(g_error), "%s: %s (%s)", where, cudaGetErrorName(err), cudaGetErrorString(err));
+    return (int)err;
+}
+
+const DeviceInfo& device_info()
+{
+    static DeviceInfo cache[64];
+    static bool have[64] = {false};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) dev = 0;
+    if (!have[dev]) {
+        DeviceInfo d;
+        d.device = dev;
+        d.sm_count = 148;
+        d.max_smem_optin = 227 * 1024;
+        cudaDeviceGetAttribute(&d.sm_count, cudaDevAttrMultiProcessorCount, dev);
+        cudaDeviceGetAttribute(&d.max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+        cache[dev] = d;
+        have[dev] = true;
+    }
+    return cache[dev];
+}
+
+}  // namespace elo
+
+extern "C" const char* elo_last_error(void) { return elo::g_error; }
+extern "C" int elo_version(void) { return 100; }

@@ -1,0 +1,217 @@
+// fused_conv_index.cu -- stand-alone projection-aware neighbour-search ops for sm_100a.
+//
+// Drop-in for the reference's native seam (file:line relative to /root/reference):
+//   FusedConvSelectKLauncher  tf_ops/2d_conv_select_k/fused_conv_g.cu:215  (kernel :11-209)
+//   FusedConvRandomKLauncher  tf_ops/2d_conv_random_k/fused_conv_g.cu:162  (kernel :13-156)
+// and for the zero-fill the op wrapper does before launching (fused_conv.cpp:154-166).
+//
+// Design (vs the reference's <<<B,256>>>, one thread per query, 60 KB of local memory per thread):
+//   * one warp per query, grid over all B*npoints queries (persistent, grid-stride), so the whole
+//     chip is busy at B = 1;
+//   * the window's scan-order offset table is built once per CTA in shared memory;
+//   * lanes test 32 window cells per step; slots and run-length counts come from ballots;
+//   * every output element is written exactly once with lane-contiguous (coalesced) stores --
+//     the kt-wide valid_* rows dominate the op's bytes, so the op is HBM-write bound
+//     (kernel K1) -- and no memset pass is needed.
+#include <cuda_runtime.h>
+#include <stdio.h>
+
+#include "../../include/elo_b200.h"
+#include "elo_common.cuh"
+#include "elo_search.cuh"
+
+namespace elo {
+
+struct IndexParams {
+    int B, H, W, N;
+    Window g;
+    const float* xyz1;
+    const float* xyz2;
+    const int* idx_n2;
+    const int* random_hw;
+    int* out_idx;      // (B, N, K, 3)
+    float* out_valid;  // (B, N, kt) or null
+    float* out_vdis;   // (B, N, kt) or null
+    float* out_mask;   // (B, N, K)
+    long long total;   // B * N
+};
+
+__device__ __forceinline__ void fill_counts(float* row, int kt, int ones, int lane)
+{
+    if (row == nullptr) return;
+    for (int i = lane; i < kt; i += 32) row[i] = i < ones ? 1.0f : 0.0f;
+}
+
+// slots [from, K): either all zero, or (b, hh, ww) with mask 1 (flag_copy)
+__device__ __forceinline__ void fill_slots(int* o_idx, float* o_mask, int from, int K, bool copy,
+                                           int b, int packed, int lane)
+{
+    const int hh = packed >> 16, ww = packed & 0xffff;
+    for (int k = from + lane; k < K; k += 32) {
+        o_idx[k * 3 + 0] = copy ? b : 0;
+        o_idx[k * 3 + 1] = copy ? hh : 0;
+        o_idx[k * 3 + 2] = copy ? ww : 0;
+        o_mask[k] = copy ? 1.0f : 0.0f;
+    }
+}
+
+template <bool SELECT>
+__global__ void __launch_bounds__(256) fused_conv_index_kernel(const IndexParams p)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const Window g = p.g;
+    int2* off = reinterpret_cast<int2*>(smem_raw);
+    const int nwarps = blockDim.x >> 5;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float* dist = nullptr;
+    int* hw = nullptr;
+    if (SELECT) {
+        float* dist_all = reinterpret_cast<float*>(off + g.kt);
+        int* hw_all = reinterpret_cast<int*>(dist_all + (size_t)nwarps * g.kt);
+        dist = dist_all + (size_t)warp * g.kt;
+        hw = hw_all + (size_t)warp * g.kt;
+    }
+    build_offsets(off, p.random_hw, g.kt, g.kH, g.kW);
+    __syncthreads();
+
+    for (long long q = (long long)blockIdx.x * nwarps + warp; q < p.total;
+         q += (long long)gridDim.x * nwarps) {
+        const int b = (int)(q / p.N);
+        const int h = __ldg(p.idx_n2 + q * 2), w = __ldg(p.idx_n2 + q * 2 + 1);
+        int* o_idx = p.out_idx + q * g.K * 3;
+        float* o_mask = p.out_mask + q * g.K;
+        float* o_valid = p.out_valid ? p.out_valid + q * g.kt : nullptr;
+        float* o_vdis = p.out_vdis ? p.out_vdis + q * g.kt : nullptr;
+
+        float xc = 0.f, yc = 0.f, zc = 0.f;
+        const bool inside = h >= 0 && h < p.H && w >= 0 && w < p.W;  // reference: out-of-range = UB
+        if (inside) {
+            const float* c = p.xyz1 + ((size_t)b * p.H * p.W + (size_t)h * p.W + w) * 3;
+            xc = __ldg(c); yc = __ldg(c + 1); zc = __ldg(c + 2);
+        }
+        // invalid centre (empty pixel): the whole row stays zero (reference :61-69)
+        if (!inside || fmaxf(sq3(xc, yc, zc), 1e-10f) <= 1e-10f) {
+            fill_slots(o_idx, o_mask, 0, g.K, false, 0, 0, lane);
+            fill_counts(o_valid, g.kt, 0, lane);
+            fill_counts(o_vdis, g.kt, 0, lane);
+            continue;
+        }
+        const float* g2 = p.xyz2 + (size_t)b * g.h2 * g.w2 * 3;
+        const int ch = h / g.stride_h, cw = w / g.stride_w;
+        auto emit = [&](int slot, int hh, int ww) {
+            o_idx[slot * 3 + 0] = b;
+            o_idx[slot * 3 + 1] = hh;
+            o_idx[slot * 3 + 2] = ww;
+            o_mask[slot] = 1.0f;
+        };
+        SearchCounts c;
+        int filled;
+        if (SELECT) {
+            c = search_select_k(g2, off, g, ch, cw, xc, yc, zc, dist, hw, &filled, emit);
+            __syncwarp();
+        } else {
+            c = search_random_k(g2, off, g, ch, cw, xc, yc, zc, emit);
+            filled = c.nsel;
+        }
+        // select-K duplicates entry 0 even when nothing was in range (mask 1, index (b,0,0));
+        // random-K only once a first neighbour was accepted (reference select :180-192, random :126-138)
+        const bool copy = g.flag_copy == 1 && (SELECT || c.nsel > 0);
+        fill_slots(o_idx, o_mask, filled, g.K, copy, b, c.first, lane);
+        fill_counts(o_valid, g.kt, c.nvalid, lane);
+        fill_counts(o_vdis, g.kt, c.nsel, lane);
+    }
+}
+
+static int launch_index(bool select, int B, int H, int W, int N, int kH, int kW, int K, int flag_copy,
+                        float distance, int stride_h, int stride_w, const float* xyz1,
+                        const float* xyz2, const int* idx_n2, const int* random_hw, int* out_idx,
+                        float* out_valid, float* out_vdis, float* out_mask, int h2, int w2,
+                        cudaStream_t stream)
+{
+    // fused_conv.cpp:79-100
+    if (N <= 0) return set_error(ELO_ERR_INVALID_ARGUMENT, "FusedConv expects positive npoints");
+    if (kH <= 0) return set_error(ELO_ERR_INVALID_ARGUMENT, "FusedConv expects positive kernel_size_H");
+    if (kW <= 0) return set_error(ELO_ERR_INVALID_ARGUMENT, "FusedConv expects positive kernel_size_W");
+    if (K <= 0) return set_error(ELO_ERR_INVALID_ARGUMENT, "FusedConv expects positive K");
+    if (flag_copy <= -1) return set_error(ELO_ERR_INVALID_ARGUMENT, "FusedConv expects 0 OR 1 flag_copy");
+    if (!(distance > 0)) return set_error(ELO_ERR_INVALID_ARGUMENT, "FusedConv expects positive distance");
+    if (stride_h <= 0) return set_error(ELO_ERR_INVALID_ARGUMENT, "FusedConv expects positive stride_h");
+    if (stride_w <= 0) return set_error(ELO_ERR_INVALID_ARGUMENT, "FusedConv expects positive stride_w");
+    if (B < 0 || H <= 0 || W <= 0 || h2 <= 0 || w2 <= 0)
+        return set_error(ELO_ERR_INVALID_ARGUMENT, "FusedConv expects positive grid extents");
+    if (!xyz1 || !xyz2 || !idx_n2 || !random_hw || !out_idx || !out_mask)
+        return set_error(ELO_ERR_INVALID_ARGUMENT, "FusedConv: null pointer");
+    const long long kt = (long long)kH * kW;
+    if (kt > 5000 || K > 5000)
+        return set_error(ELO_ERR_UNSUPPORTED, "FusedConv: kernel_size_H*kernel_size_W and K are limited to 5000");
+    if (H >= 32768 || W >= 32768 || h2 >= 32768 || w2 >= 32768)
+        return set_error(ELO_ERR_UNSUPPORTED, "FusedConv: grid extents are limited to 32767");
+    if (B == 0) return ELO_OK;
+
+    IndexParams p;
+    p.B = B; p.H = H; p.W = W; p.N = N;
+    p.g.h2 = h2; p.g.w2 = w2; p.g.kH = kH; p.g.kW = kW; p.g.kt = (int)kt;
+    p.g.stride_h = stride_h; p.g.stride_w = stride_w; p.g.K = K; p.g.flag_copy = flag_copy;
+    p.g.d2max = distance * distance;
+    p.xyz1 = xyz1; p.xyz2 = xyz2; p.idx_n2 = idx_n2; p.random_hw = random_hw;
+    p.out_idx = out_idx; p.out_valid = out_valid; p.out_vdis = out_vdis; p.out_mask = out_mask;
+    p.total = (long long)B * N;
+
+    int warps = 8;
+    size_t smem = (size_t)kt * sizeof(int2);
+    if (select) {
+        const size_t per_warp = (size_t)kt * 8;
+        const size_t budget = 200 * 1024 - smem;
+        while (warps > 1 && per_warp * warps > budget) warps >>= 1;
+        smem += per_warp * warps;
+    }
+    const DeviceInfo& dev = device_info();
+    long long ctas = (p.total + warps - 1) / warps;
+    const long long resident = (long long)dev.sm_count * (select ? 4 : 8);
+    if (ctas > resident) ctas = resident;
+
+    cudaError_t err;
+    if (select) {
+        if (smem > 48 * 1024) {
+            err = cudaFuncSetAttribute(fused_conv_index_kernel<true>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (err != cudaSuccess) return set_cuda_error(err, "cudaFuncSetAttribute(select_k)");
+        }
+        fused_conv_index_kernel<true><<<(unsigned)ctas, warps * 32, smem, stream>>>(p);
+    } else {
+        fused_conv_index_kernel<false><<<(unsigned)ctas, warps * 32, smem, stream>>>(p);
+    }
+    err = cudaGetLastError();
+    if (err != cudaSuccess) return set_cuda_error(err, select ? "fused_conv_select_k launch" : "fused_conv_random_k launch");
+    return ELO_OK;
+}
+
+}  // namespace elo
+
+extern "C" int elo_fused_conv_select_k(int batch_size, int H, int W, int npoints, int kernel_size_H,
+                                       int kernel_size_W, int K, int flag_copy, float distance,
+                                       int stride_h, int stride_w, const float* xyz1,
+                                       const float* xyz2, const int* idx_n2, const int* random_hw,
+                                       int* selected_bhw_idx, float* valid_idx,
+                                       float* valid_in_dis_idx, float* selected_mask, int small_h,
+                                       int small_w, void* stream)
+{
+    return elo::launch_index(true, batch_size, H, W, npoints, kernel_size_H, kernel_size_W, K,
+                             flag_copy, distance, stride_h, stride_w, xyz1, xyz2, idx_n2, random_hw,
+                             selected_bhw_idx, valid_idx, valid_in_dis_idx, selected_mask, small_h,
+                             small_w, (cudaStream_t)stream);
+}
+
+extern "C" int elo_fused_conv_random_k(int batch_size, int H, int W, int npoints, int kernel_size_H,
+                                       int kernel_size_W, int K, int flag_copy, float distance,
+                                       int stride_h, int stride_w, const float* xyz1,
+                                       const float* xyz2, const int* idx_n2, const int* random_hw,
+                                       int* selected_bhw_idx, float* valid_idx,
+                                       float* valid_in_dis_idx, float* selected_mask, int small_h,
+                                       int small_w, void* stream)
+{
+    return elo::launch_index(false, batch_size, H, W, npoints, kernel_size_H, kernel_size_W, K,
+                             flag_copy, distance, stride_h, stride_w, xyz1, xyz2, idx_n2, random_hw,
+                             selected_bhw_idx, valid_idx, valid_in_dis_idx, selected_mask, small_h,
+                             small_w, (cudaStream_t)stream);
+}

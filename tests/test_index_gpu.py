@@ -1,0 +1,183 @@
+"""GPU: the CUDA index ops, called through the C ABI, against the oracle -- bit-exact on all four
+outputs (selected_bhw_idx, valid_idx, valid_in_dis_idx, selected_mask)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import cases
+from oracle import index_oracle as io
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden", "index_golden.npz")
+
+
+def run_cuda(elo, cuda, mode, xyz1, xyz2, idx_n2, random_hw, H, W, npoints, kH, kW, K, flag_copy,
+             distance, sh, sw):
+    fn = elo.fused_conv_select_k if mode == "select" else elo.fused_conv_random_k
+    t = lambda a: torch.as_tensor(np.ascontiguousarray(a)).to(cuda)
+    outs = fn(t(xyz1), t(xyz2), t(idx_n2), t(random_hw), H, W, npoints, kH, kW, K, flag_copy, distance, sh, sw)
+    torch.cuda.synchronize()
+    return tuple(o.cpu().numpy() for o in outs)
+
+
+def cuda_impl(elo, cuda):
+    return lambda mode, *a, **k: run_cuda(elo, cuda, mode, *a, **k)
+
+
+def test_demo_known_answers(elo, cuda):
+    H, W = 4, 7
+    xyz = np.tile(np.arange(H * W, dtype=np.float32).reshape(1, H, W, 1), (1, 1, 1, 3))
+    idx = np.array([[[0, 0], [0, 1]]], np.int32)
+    for mode, rhw, cols in [("select", [0, 1, 2, 3, 4], [1, 2, 3, 6]), ("select", [3, 0, 4, 2, 1], [1, 2, 3, 6]),
+                            ("random", [0, 1, 2, 3, 4], [6, 1, 2, 3]), ("random", [3, 0, 4, 2, 1], [2, 6, 3, 1])]:
+        sel, valid, vdis, mask = run_cuda(elo, cuda, mode, xyz, xyz, idx, np.array(rhw, np.int32), H, W, 2, 1, 5, 8, 0, 200.0, 1, 1)
+        assert not sel[0, 0].any() and not valid[0, 0].any() and not vdis[0, 0].any() and not mask[0, 0].any()
+        assert sel[0, 1, :, 2].tolist() == cols + [0, 0, 0, 0]
+        assert mask[0, 1, :, 0].tolist() == [1, 1, 1, 1, 0, 0, 0, 0]
+        assert valid[0, 1, :, 0].tolist() == [1, 1, 1, 1, 0] and vdis[0, 1, :, 0].tolist() == [1, 1, 1, 1, 0]
+
+
+def test_select_k_tie_order(elo, cuda):
+    W = 8
+    xyz = np.zeros((1, 1, W, 3), np.float32)
+    xyz[0, 0, :, 0] = [11, 10, 9, 50, 60, 70, 80, 90]
+    xyz[0, 0, :, 1] = 1
+    idx = np.array([[[0, 1]]], np.int32)
+    sel, _, _, mask = run_cuda(elo, cuda, "select", xyz, xyz, idx, np.array([0, 2, 1], np.int32), 1, W, 1, 1, 3, 3, 0, 1000.0, 1, 1)
+    assert sel[0, 0, :, 2].tolist() == [1, 2, 0] and mask[0, 0, :, 0].tolist() == [1, 1, 1]
+
+
+@pytest.mark.parametrize("chunk", range(8))
+def test_random_cases_vs_oracle(elo, cuda, chunk):
+    for seed in range(chunk * 40, chunk * 40 + 40):
+        case = cases.random_case(np.random.default_rng(seed))
+        cases.assert_same(cases.call(cuda_impl(elo, cuda), case), cases.call(io.port, case), "seed %d" % seed)
+
+
+@pytest.mark.parametrize("chunk", range(4))
+def test_tie_heavy_integer_cases_vs_oracle(elo, cuda, chunk):
+    for seed in range(5000 + chunk * 40, 5000 + chunk * 40 + 40):
+        case = cases.random_case(np.random.default_rng(seed), integer=True)
+        cases.assert_same(cases.call(cuda_impl(elo, cuda), case), cases.call(io.port, case), "seed %d" % seed)
+
+
+@pytest.mark.parametrize("site", cases.MODEL_SITES, ids=lambda s: s[0])
+def test_model_sites_vs_oracle_and_reference_kernel(elo, cuda, site):
+    rng = np.random.default_rng(abs(hash(site[0])) % (2 ** 31))
+    case = cases.site_case(rng, site, B=2)
+    got = cases.call(cuda_impl(elo, cuda), case)
+    cases.assert_same(got, cases.call(io.port, case, nthreads=8), site[0] + " vs port")
+    if io.have_ref_gpu():
+        c = dict(case)
+        for k in ("xyz1", "xyz2", "idx_n2", "random_hw"):
+            c[k] = torch.as_tensor(c[k]).to(cuda)
+        ref = tuple(o.cpu().numpy() for o in cases.call(io.ref_gpu, c))
+        cases.assert_same(got, ref, site[0] + " vs reference .cu")
+
+
+def test_golden_vectors(elo, cuda):
+    g = np.load(GOLDEN)
+    for i in range(int(g["n_cases"])):
+        p = "c%d_" % i
+        case = dict(mode=str(g[p + "mode"]), xyz1=g[p + "xyz1"], xyz2=g[p + "xyz2"], idx_n2=g[p + "idx_n2"],
+                    random_hw=g[p + "random_hw"], distance=float(g[p + "distance"]))
+        for k, v in zip(("H", "W", "npoints", "kernel_size_H", "kernel_size_W", "K", "flag_copy",
+                         "stride_h", "stride_w"), g[p + "ints"].tolist()):
+            case[k] = int(v)
+        cases.assert_same(cases.call(cuda_impl(elo, cuda), case), tuple(g[p + n] for n in cases.OUT_NAMES), "golden %d" % i)
+
+
+def test_nonfinite_inputs_match_reference_kernel(elo, cuda):
+    if not io.have_ref_gpu():
+        pytest.skip("oracle/_ref/libref_gpu.so not built")
+    rng = np.random.default_rng(3)
+    case = cases.site_case(rng, cases.MODEL_SITES[6], B=1)
+    for arr in (case["xyz1"], case["xyz2"]):
+        flat = arr.reshape(-1)
+        pos = rng.choice(flat.size, 40, replace=False)
+        flat[pos[:20]] = np.nan
+        flat[pos[20:30]] = np.inf
+        flat[pos[30:]] = -np.inf
+    got = cases.call(cuda_impl(elo, cuda), case)
+    c = dict(case)
+    for k in ("xyz1", "xyz2", "idx_n2", "random_hw"):
+        c[k] = torch.as_tensor(c[k]).to(cuda)
+    ref = tuple(o.cpu().numpy() for o in cases.call(io.ref_gpu, c))
+    cases.assert_same(got, ref, "non-finite")
+
+
+@pytest.mark.parametrize("kH,kW", [(7, 25), (11, 41)])
+def test_config1_full_frame_select_k(elo, cuda, kH, kW):
+    """BASELINE.json configs[0]: one 64x1800 synthetic frame, K=16, every cell a query."""
+    H, W, K = 64, 1800, 16
+    xyz = elo.synth.synth_scan(H, W, seed=0)[None]
+    idx = elo.synth.hw_index(1, H, W)
+    rhw = torch.randperm(kH * kW, generator=torch.Generator().manual_seed(0)).to(torch.int32)
+    got = run_cuda(elo, cuda, "select", xyz.numpy(), xyz.numpy(), idx.numpy(), rhw.numpy(), H, W, H * W, kH, kW, K, 0, 1000.0, 1, 1)
+    want = io.port("select", xyz.numpy(), xyz.numpy(), idx.numpy(), rhw.numpy(), H, W, H * W, kH, kW, K, 0, 1000.0, 1, 1,
+                   nthreads=os.cpu_count() or 1)
+    cases.assert_same(got, want, "config 1 %dx%d" % (kH, kW))
+    # size-independent properties: masks are a prefix of ones, counts are run lengths with
+    # nsel <= nvalid, every selected cell is a non-empty pixel, distances are non-decreasing,
+    # and the nearest neighbour of a valid pixel searched in its own frame is itself.
+    sel, valid, vdis, mask = got
+    m = mask[0, :, :, 0]
+    assert ((m[:, :-1] >= m[:, 1:]).all())
+    v, d = valid[0, :, :, 0], vdis[0, :, :, 0]
+    assert (v[:, :-1] >= v[:, 1:]).all() and (d[:, :-1] >= d[:, 1:]).all() and (d.sum(1) <= v.sum(1)).all()
+    assert (np.minimum(d.sum(1), K) == m.sum(1)).all()
+    g = xyz[0].numpy()
+    pts = g[sel[0, :, :, 1], sel[0, :, :, 2]]
+    centre = g.reshape(-1, 3)
+    assert (np.abs(pts).sum(-1)[m > 0] > 0).all()
+    dist = ((pts - centre[:, None, :]) ** 2).sum(-1)
+    dist = np.where(m > 0, dist, np.inf)
+    assert (dist[:, :-1] <= dist[:, 1:] * (1 + 1e-5) + 1e-9).all()
+    ok = np.abs(centre).sum(-1) > 0
+    own = np.stack([idx[0, :, 0].numpy(), idx[0, :, 1].numpy()], -1)
+    assert (sel[0, ok, 0, 1:] == own[ok]).all()
+
+
+def test_optional_count_outputs_and_graph_capture(elo, cuda):
+    rng = np.random.default_rng(9)
+    case = cases.site_case(rng, cases.MODEL_SITES[8], B=2)
+    t = {k: torch.as_tensor(case[k]).to(cuda) for k in ("xyz1", "xyz2", "idx_n2", "random_hw")}
+    full = elo.fused_conv_select_k(t["xyz1"], t["xyz2"], t["idx_n2"], t["random_hw"], case["H"], case["W"],
+                                   case["npoints"], 7, 25, 6, 0, 1000.0, 1, 1)
+    idx2, mask2 = elo.fused_conv_indices(True, t["xyz1"], t["xyz2"], t["idx_n2"], t["random_hw"], 7, 25, 6, 0, 1000.0, 1, 1)
+    assert torch.equal(full[0], idx2) and torch.equal(full[3], mask2)
+    # no allocation / sync / host read inside the C ABI call: it can be captured in a CUDA graph
+    lib = elo._lib.lib()
+    out_idx = torch.full_like(full[0], -7)
+    out_mask = torch.full_like(full[3], -7)
+    stream = torch.cuda.Stream()
+    graph = torch.cuda.CUDAGraph()
+    torch.cuda.synchronize()
+    with torch.cuda.graph(graph, stream=stream):
+        rc = lib.elo_fused_conv_select_k(2, case["H"], case["W"], case["npoints"], 7, 25, 6, 0, 1000.0, 1, 1,
+                                         t["xyz1"].data_ptr(), t["xyz2"].data_ptr(), t["idx_n2"].data_ptr(),
+                                         t["random_hw"].data_ptr(), out_idx.data_ptr(), None, None,
+                                         out_mask.data_ptr(), case["H"], case["W"],
+                                         torch.cuda.current_stream().cuda_stream)
+        assert rc == 0
+    graph.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(out_idx, full[0]) and torch.equal(out_mask, full[3])
+
+
+def test_argument_errors_follow_the_reference_op(elo, cuda):
+    z = torch.zeros(1, 4, 8, 3, device=cuda)
+    idx = torch.zeros(1, 2, 2, dtype=torch.int32, device=cuda)
+    rhw = torch.arange(9, dtype=torch.int32, device=cuda)
+    ok = dict(H=4, W=8, npoints=2, kernel_size_H=3, kernel_size_W=3, K=4, flag_copy=0, distance=1.0, stride_h=1, stride_w=1)
+    elo.fused_conv_random_k(z, z, idx, rhw, **ok)
+    for bad in (dict(K=0), dict(distance=0.0), dict(distance=-1.0), dict(flag_copy=-1), dict(stride_h=0),
+                dict(kernel_size_H=0), dict(npoints=3), dict(kernel_size_W=5)):
+        with pytest.raises(ValueError):
+            elo.fused_conv_random_k(z, z, idx, rhw, **{**ok, **bad})
+    with pytest.raises(ValueError):
+        elo.fused_conv_select_k(z[..., :2], z, idx, rhw, **ok)
+    with pytest.raises(ValueError):                      # xyz2 must have ceil(H/stride_h) rows
+        elo.fused_conv_select_k(z, z, idx, rhw, **{**ok, "stride_h": 2})
