@@ -9,11 +9,77 @@ from .build import LIB
 
 _c_int, _c_float, _c_void_p = ctypes.c_int, ctypes.c_float, ctypes.c_void_p
 
+_c_ll, _c_uint = ctypes.c_longlong, ctypes.c_uint
+
+
+# ---- descriptor structs, field for field as in include/elo_b200.h --------------------------------
+class Window(ctypes.Structure):
+    _fields_ = [("kernel_size_H", _c_int), ("kernel_size_W", _c_int), ("K", _c_int), ("distance", _c_float),
+                ("stride_h", _c_int), ("stride_w", _c_int), ("small_h", _c_int), ("small_w", _c_int),
+                ("random_hw", _c_void_p)]
+
+
+class Queries(ctypes.Structure):
+    _fields_ = [("H", _c_int), ("W", _c_int), ("out_h", _c_int), ("out_w", _c_int),
+                ("q_stride_h", _c_int), ("q_stride_w", _c_int)]
+
+
+class GroupMlpDesc(ctypes.Structure):
+    _fields_ = [("batch_size", _c_int), ("queries", Queries), ("nsets", _c_int), ("set_batch_offset", _c_int * 2),
+                ("window", Window * 2), ("feat_channels", _c_int), ("num_layers", _c_int), ("cout", _c_int * 3),
+                ("xyz1", _c_void_p), ("xyz2", _c_void_p), ("feat2", _c_void_p * 2), ("weights", _c_void_p * 2),
+                ("out", _c_void_p * 2), ("dbg_nbr", _c_void_p * 2)]
+
+
+class CostVolumeDesc(ctypes.Structure):
+    _fields_ = [("batch_size", _c_int), ("H", _c_int), ("W", _c_int), ("C", _c_int),
+                ("window_q", Window), ("window_p", Window),
+                ("xyz1", _c_void_p), ("xyz2", _c_void_p), ("f1", _c_void_p), ("f2", _c_void_p),
+                ("weights_1", _c_void_p), ("weights_2", _c_void_p), ("stage1_out", _c_void_p), ("out", _c_void_p),
+                ("dbg_nbr_q", _c_void_p), ("dbg_nbr_p", _c_void_p)]
+
+
+class RowMlpPhase(ctypes.Structure):
+    _fields_ = [("num_sources", _c_int), ("channels", _c_int * 3), ("from_previous", _c_int * 3),
+                ("num_layers", _c_int), ("cout", _c_int * 3), ("src", (_c_void_p * 3) * 2)]
+
+
+class RowMlpDesc(ctypes.Structure):
+    _fields_ = [("rows", _c_ll), ("nsets", _c_int), ("num_phases", _c_int), ("phase", RowMlpPhase * 2),
+                ("weights", _c_void_p * 2), ("out", _c_void_p * 2), ("out_phase0", _c_void_p * 2)]
+
+
+class ProjectDesc(ctypes.Structure):
+    _fields_ = [("batch_size", _c_int), ("num_points", _c_int), ("H", _c_int), ("W", _c_int), ("C", _c_int),
+                ("mode", _c_int), ("points", _c_void_p), ("point_stride", _c_ll), ("batch_stride", _c_ll),
+                ("inner_batch", _c_int), ("outer_stride", _c_ll), ("feat", _c_void_p),
+                ("T", _c_void_p), ("q", _c_void_p), ("t", _c_void_p),
+                ("pi", _c_float), ("az_res", _c_float), ("v_res", _c_float), ("v_off", _c_float),
+                ("cellmin", _c_void_p), ("out_xyz", _c_void_p), ("out_feat", _c_void_p), ("out_points", _c_void_p)]
+
+
+class PoseHeadDesc(ctypes.Structure):
+    _fields_ = [("batch_size", _c_int), ("num_points", _c_int), ("num_slices", _c_int), ("has_coarse", _c_int),
+                ("feature", _c_void_p), ("weight", _c_void_p), ("xyz", _c_void_p),
+                ("w_big", _c_void_p), ("b_big", _c_void_p), ("w_q", _c_void_p), ("b_q", _c_void_p),
+                ("w_t", _c_void_p), ("b_t", _c_void_p), ("q_coarse", _c_void_p), ("t_coarse", _c_void_p),
+                ("partial", _c_void_p), ("counter", _c_void_p),
+                ("q_out", _c_void_p), ("t_out", _c_void_p), ("q_norm_out", _c_void_p), ("pooled_out", _c_void_p)]
+
+
 # name -> argtypes; every function returns int (0 = ok), see include/elo_b200.h
 _FUSED_CONV = [_c_int] * 8 + [_c_float, _c_int, _c_int] + [_c_void_p] * 8 + [_c_int, _c_int, _c_void_p]
 SIGNATURES = {
     "elo_fused_conv_select_k": _FUSED_CONV,
     "elo_fused_conv_random_k": _FUSED_CONV,
+    "elo_group_mlp_max": [ctypes.POINTER(GroupMlpDesc), _c_void_p],
+    "elo_set_conv_small": [ctypes.POINTER(GroupMlpDesc), _c_void_p],
+    "elo_cost_volume_1": [ctypes.POINTER(CostVolumeDesc), _c_void_p],
+    "elo_cost_volume_2": [ctypes.POINTER(CostVolumeDesc), _c_void_p],
+    "elo_row_mlp": [ctypes.POINTER(RowMlpDesc), _c_void_p],
+    "elo_project": [ctypes.POINTER(ProjectDesc), _c_void_p],
+    "elo_pose_head": [ctypes.POINTER(PoseHeadDesc), _c_void_p],
+    "elo_gt_pose": [_c_int, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p],
 }
 
 _lib = None
@@ -59,3 +125,17 @@ def stream_ptr(device):
 
 def ptr(t):
     return None if t is None else t.data_ptr()
+
+
+def call(name, desc, device):
+    """Launch one descriptor-style entry point on torch's current stream of `device`."""
+    import torch
+    with torch.cuda.device(device):
+        rc = getattr(lib(), name)(ctypes.byref(desc), stream_ptr(device))
+    check(rc, name)
+
+
+def require_cuda(name, *tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise EloError("%s: tensor on %s; this path only runs on CUDA (no CPU fallback)" % (name, t.device))

@@ -1,0 +1,741 @@
+// fused_blocks.cu -- the neighbour-search -> gather -> shared-MLP -> pool blocks of the network, each
+// as ONE kernel whose (B,N,K,C) intermediates never reach HBM (sm_100a).
+//
+//   elo_group_mlp_max   set-conv / first half of set-upconv   utils/pointnet_util.py:197-230, 272-298
+//   elo_cost_volume_1   cost volume, point-to-patch stage      utils/pointnet_util.py:45-100
+//   elo_cost_volume_2   cost volume, patch-to-patch stage      utils/pointnet_util.py:104-146
+//   elo_row_mlp         per-point MLP chains                   utils/pointnet_util.py:153-175, 303-311
+//
+// Every kernel: (1) one thread starts the weight stream (TMA bulk copies, elo_mlp.cuh) so the first
+// chunks land while (2) warps run the projection-aware neighbour search of the tile's queries
+// (elo_search.cuh, same code as the stand-alone index ops) and (3) all threads gather xyz / features
+// of the selected cells into the swizzled [channel][row] tile; (4) the layers run back to back out
+// of shared memory; (5) the reduction over the K neighbours (max, or masked softmax-weighted sum)
+// writes (B,N,C_out) once.  Inference batch-norm is folded into the weights on the host.
+#include <cuda_runtime.h>
+#include <math.h>
+
+#include "../../include/elo_b200.h"
+#include "elo_common.cuh"
+#include "elo_tile.cuh"
+
+namespace elo {
+
+static constexpr int SMEM_LIMIT = 227 * 1024;
+
+// ================================================================================================
+// group_mlp_max
+struct GroupMlpParams {
+    QuerySet qs;
+    Window g;
+    long long q_base[2], q_end[2];   // global query range of each parameter set
+    int qt, Cf, nl, cout[3], total_chunks;
+    const float* xyz1;
+    const float* xyz2;
+    const float* feat2[2];
+    const int* random_hw[2];
+    const float* weights[2];
+    float* out[2];
+    int* dbg_nbr[2];
+};
+
+template <int NB>
+__global__ void __launch_bounds__(CTA_THREADS, 1) group_mlp_max_kernel(const GroupMlpParams p)
+{
+    constexpr int RS = NB * 64;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    SmemCarver sc(smem_raw);
+    float* ring = sc.take<float>(RING * CHUNK_FLOATS);
+    uint64_t* bars = sc.take<uint64_t>(RING);
+    int2* off = sc.take<int2>(p.g.kt);
+    int* nbr = sc.take<int>(RS);
+    float* ctr = sc.take<float>(RS * 4);
+    const int cin0 = 3 + p.Cf;
+    float* X = sc.take<float>((size_t)((cin0 + 3) & ~3) * RS);
+    float* A = sc.take<float>(128 * RS);
+    float* Bf = sc.take<float>(128 * RS);
+
+    const int set = blockIdx.y;
+    const Window g = p.g;
+    WeightStream ws;
+    ws.start(p.weights[set], ring, bars, p.total_chunks, 1);
+    build_offsets(off, p.random_hw[set], g.kt, g.kH, g.kW);
+    for (int i = threadIdx.x; i < RS; i += blockDim.x) nbr[i] = -1;
+    __syncthreads();
+
+    const long long q0 = p.q_base[set] + (long long)blockIdx.x * p.qt;
+    const long long total_q = p.q_end[set];
+    const int cells2 = g.h2 * g.w2;
+    tile_search<false>(p.qs, g, p.xyz1, p.xyz2, off, q0, p.qt, total_q, nbr, ctr, nullptr, nullptr);
+    __syncthreads();
+
+    // first layer input: [q_k - p (3), feat2_k (Cf)], masked neighbours contribute q = 0, feat = 0
+    for (int r = threadIdx.x; r < RS; r += blockDim.x) {
+        const int q = r / g.K;
+        float dx = 0.f, dy = 0.f, dz = 0.f;
+        if (q < p.qt) {
+            const int b = __float_as_int(ctr[q * 4 + 3]);
+            if (b >= 0) {
+                float qx = 0.f, qy = 0.f, qz = 0.f;
+                const int cell = nbr[r];
+                if (cell >= 0) {
+                    const float* s = p.xyz2 + ((size_t)b * cells2 + cell) * 3;
+                    qx = __ldg(s); qy = __ldg(s + 1); qz = __ldg(s + 2);
+                }
+                dx = qx - ctr[q * 4 + 0]; dy = qy - ctr[q * 4 + 1]; dz = qz - ctr[q * 4 + 2];
+            }
+        }
+        X[act_index(0, r, RS)] = dx;
+        X[act_index(1, r, RS)] = dy;
+        X[act_index(2, r, RS)] = dz;
+    }
+    {
+        const float* feat = p.feat2[set];
+        const int K = g.K, qt = p.qt;
+        gather_features(X, RS, 3, feat, p.Cf, RS, [&](int r) -> long long {
+            const int q = r / K;
+            if (q >= qt || nbr[r] < 0) return -1;
+            return (long long)__float_as_int(ctr[q * 4 + 3]) * cells2 + nbr[r];
+        });
+    }
+    __syncthreads();
+
+    const float* in = X;
+    int cin = cin0;
+    for (int l = 0; l < p.nl; ++l) {
+        float* o = (l & 1) ? Bf : A;
+        dense_rt<NB>(ws, in, cin, o, p.cout[l]);
+        in = o;
+        cin = p.cout[l];
+    }
+
+    // max over the K neighbours of (y * mask): y >= 0 after ReLU, masked rows count as 0
+    const int Cout = cin;
+    float* out = p.out[set];
+    for (int t = threadIdx.x; t < p.qt * Cout; t += blockDim.x) {
+        const int q = t / Cout, c = t - q * Cout;
+        const long long gq = q0 + q;
+        if (gq >= total_q) break;
+        float m = 0.f;
+        for (int k = 0; k < g.K; ++k)
+            if (nbr[q * g.K + k] >= 0) m = fmaxf(m, in[act_index(c, q * g.K + k, RS)]);
+        out[gq * Cout + c] = m;
+    }
+    if (p.dbg_nbr[set] != nullptr)
+        for (int t = threadIdx.x; t < p.qt * g.K; t += blockDim.x)
+            if (q0 + t / g.K < total_q) p.dbg_nbr[set][q0 * g.K + t] = nbr[t];
+}
+
+// ================================================================================================
+// cost volume, stage 1 (point-to-patch)
+struct Cv1Params {
+    QuerySet qs;
+    Window g;
+    long long total_q;
+    int qt, C, total_chunks;
+    const float* xyz1;
+    const float* xyz2;
+    const float* f1;
+    const float* f2;
+    const int* random_hw;
+    const float* weights;
+    float* out;
+    int* dbg_nbr;
+};
+
+// xyz part of a cost-volume row: [p, q, q - p, sqrt(|q - p|^2 + 1e-20)] (utils/pointnet_util.py:60-63)
+__device__ __forceinline__ void write_xyz10(float* X, int RS, int r, float px, float py, float pz, float qx,
+                                            float qy, float qz)
+{
+    const float dx = qx - px, dy = qy - py, dz = qz - pz;
+    X[act_index(0, r, RS)] = px; X[act_index(1, r, RS)] = py; X[act_index(2, r, RS)] = pz;
+    X[act_index(3, r, RS)] = qx; X[act_index(4, r, RS)] = qy; X[act_index(5, r, RS)] = qz;
+    X[act_index(6, r, RS)] = dx; X[act_index(7, r, RS)] = dy; X[act_index(8, r, RS)] = dz;
+    X[act_index(9, r, RS)] = sqrtf(__fadd_rn(sumsq_tf(dx, dy, dz), 1e-20f));
+}
+
+// masked softmax over the K rows of a query, per channel, applied to `val` (TF: where(mask, w, -1e10),
+// softmax(dim=2), reduce_sum(w * val)).  An all-masked group gets uniform weights 1/K.
+__device__ __forceinline__ float softmax_pool(const float* logit, const float* val, const int* nbr_row, int c,
+                                              int row0, int K, int RS)
+{
+    float m = -INFINITY;
+    for (int k = 0; k < K; ++k) {
+        const float l = nbr_row[k] >= 0 ? logit[act_index(c, row0 + k, RS)] : -1e10f;
+        m = fmaxf(m, l);
+    }
+    float s = 0.f, acc = 0.f;
+    for (int k = 0; k < K; ++k) {
+        const float l = nbr_row[k] >= 0 ? logit[act_index(c, row0 + k, RS)] : -1e10f;
+        const float e = expf(l - m);
+        s += e;
+        acc = fmaf(e, val[act_index(c, row0 + k, RS)], acc);
+    }
+    return acc / s;
+}
+
+template <int NB>
+__global__ void __launch_bounds__(CTA_THREADS, 1) cost_volume_1_kernel(const Cv1Params p)
+{
+    constexpr int RS = NB * 64;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    SmemCarver sc(smem_raw);
+    float* ring = sc.take<float>(RING * CHUNK_FLOATS);
+    uint64_t* bars = sc.take<uint64_t>(RING);
+    int2* off = sc.take<int2>(p.g.kt);
+    int* nbr = sc.take<int>(RS);
+    float* ctr = sc.take<float>(RS * 4);
+    const int C = p.C, xc = 10 + 2 * C;
+    float* X = sc.take<float>((size_t)((xc + 3) & ~3) * RS);
+    float* A = sc.take<float>(128 * RS);     // A, Bf, Cb are contiguous: the select-K scratch aliases them
+    float* Bf = sc.take<float>(128 * RS);
+    float* Cb = sc.take<float>(64 * RS);
+
+    const Window g = p.g;
+    WeightStream ws;
+    ws.start(p.weights, ring, bars, p.total_chunks, 1);
+    build_offsets(off, p.random_hw, g.kt, g.kH, g.kW);
+    for (int i = threadIdx.x; i < RS; i += blockDim.x) nbr[i] = -1;
+    __syncthreads();
+
+    const long long q0 = (long long)blockIdx.x * p.qt;
+    const int cells = g.h2 * g.w2, nwarps = blockDim.x >> 5;
+    float* sdist = A;
+    int* shw = reinterpret_cast<int*>(A + (size_t)nwarps * g.kt);
+    tile_search<true>(p.qs, g, p.xyz1, p.xyz2, off, q0, p.qt, p.total_q, nbr, ctr, sdist, shw);
+    __syncthreads();
+
+    for (int r = threadIdx.x; r < RS; r += blockDim.x) {
+        const int q = r / g.K;
+        float px = 0.f, py = 0.f, pz = 0.f, qx = 0.f, qy = 0.f, qz = 0.f;
+        if (q < p.qt) {
+            const int b = __float_as_int(ctr[q * 4 + 3]);
+            if (b >= 0) {
+                px = ctr[q * 4 + 0]; py = ctr[q * 4 + 1]; pz = ctr[q * 4 + 2];
+                const int cell = nbr[r];
+                if (cell >= 0) {
+                    const float* s = p.xyz2 + ((size_t)b * cells + cell) * 3;
+                    qx = __ldg(s); qy = __ldg(s + 1); qz = __ldg(s + 2);
+                }
+            }
+        }
+        write_xyz10(X, RS, r, px, py, pz, qx, qy, qz);
+    }
+    {
+        const int K = g.K, qt = p.qt, nq = p.qs.oh * p.qs.ow;
+        const long long total = p.total_q;
+        // f1 of the query pixel, repeated for its K rows (queries are all pixels: linear cell = gq)
+        gather_features(X, RS, 10, p.f1, C, RS, [&](int r) -> long long {
+            const int q = r / K;
+            return (q < qt && q0 + q < total) ? q0 + q : -1;
+        });
+        gather_features(X, RS, 10 + C, p.f2, C, RS, [&](int r) -> long long {
+            const int q = r / K;
+            if (q >= qt || nbr[r] < 0) return -1;
+            return (long long)((q0 + q) / nq) * cells + nbr[r];
+        });
+    }
+    __syncthreads();
+
+    dense<NB, 128, true>(ws, X, xc, A);            // CV_0
+    dense<NB, 64, true>(ws, A, 128, Cb);           // CV_1
+    dense<NB, 64, true>(ws, Cb, 64, Bf + 64 * RS); // CV_2      -> F   = Bf[64:128]
+    dense<NB, 64, true>(ws, X, 10, Bf);            // CV_xyz    -> enc = Bf[0:64]
+    dense<NB, 128, true>(ws, Bf, 128, A);          // sum_CV_0 on [enc, F]
+    dense<NB, 64, true>(ws, A, 128, Cb);           // sum_CV_1  -> attention logits
+
+    for (int t = threadIdx.x; t < p.qt * 64; t += blockDim.x) {
+        const int q = t >> 6, c = t & 63;
+        const long long gq = q0 + q;
+        if (gq >= p.total_q) break;
+        p.out[gq * 64 + c] = softmax_pool(Cb, Bf + 64 * RS, nbr + q * g.K, c, q * g.K, g.K, RS);
+    }
+    if (p.dbg_nbr != nullptr)
+        for (int t = threadIdx.x; t < p.qt * g.K; t += blockDim.x)
+            if (q0 + t / g.K < p.total_q) p.dbg_nbr[q0 * g.K + t] = nbr[t];
+}
+
+// ================================================================================================
+// cost volume, stage 2 (patch-to-patch)
+struct Cv2Params {
+    QuerySet qs;
+    Window g;
+    long long total_q;
+    int qt, C, total_chunks;
+    const float* xyz1;
+    const float* f1;
+    const float* cv1;
+    const int* random_hw;
+    const float* weights;
+    float* out;
+    int* dbg_nbr;
+};
+
+template <int NB>
+__global__ void __launch_bounds__(CTA_THREADS, 1) cost_volume_2_kernel(const Cv2Params p)
+{
+    constexpr int RS = NB * 64;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    SmemCarver sc(smem_raw);
+    float* ring = sc.take<float>(RING * CHUNK_FLOATS);
+    uint64_t* bars = sc.take<uint64_t>(RING);
+    int2* off = sc.take<int2>(p.g.kt);
+    int* nbr = sc.take<int>(RS);
+    float* ctr = sc.take<float>(RS * 4);
+    const int C = p.C;
+    float* Y = sc.take<float>(12 * RS);
+    float* X = sc.take<float>((size_t)(128 + C) * RS);
+    float* A = sc.take<float>(128 * RS);
+    float* Cb = sc.take<float>(64 * RS);
+
+    const Window g = p.g;
+    WeightStream ws;
+    ws.start(p.weights, ring, bars, p.total_chunks, 1);
+    build_offsets(off, p.random_hw, g.kt, g.kH, g.kW);
+    for (int i = threadIdx.x; i < RS; i += blockDim.x) nbr[i] = -1;
+    __syncthreads();
+
+    const long long q0 = (long long)blockIdx.x * p.qt;
+    const int cells = g.h2 * g.w2;
+    tile_search<false>(p.qs, g, p.xyz1, p.xyz1, off, q0, p.qt, p.total_q, nbr, ctr, nullptr, nullptr);
+    __syncthreads();
+
+    for (int r = threadIdx.x; r < RS; r += blockDim.x) {
+        const int q = r / g.K;
+        float px = 0.f, py = 0.f, pz = 0.f, qx = 0.f, qy = 0.f, qz = 0.f;
+        if (q < p.qt) {
+            const int b = __float_as_int(ctr[q * 4 + 3]);
+            if (b >= 0) {
+                px = ctr[q * 4 + 0]; py = ctr[q * 4 + 1]; pz = ctr[q * 4 + 2];
+                const int cell = nbr[r];
+                if (cell >= 0) {
+                    const float* s = p.xyz1 + ((size_t)b * cells + cell) * 3;
+                    qx = __ldg(s); qy = __ldg(s + 1); qz = __ldg(s + 2);
+                }
+            }
+        }
+        write_xyz10(Y, RS, r, px, py, pz, qx, qy, qz);
+    }
+    {
+        const int K = g.K, qt = p.qt, nq = p.qs.oh * p.qs.ow;
+        const long long total = p.total_q;
+        gather_features(X, RS, 64, p.f1, C, RS, [&](int r) -> long long {
+            const int q = r / K;
+            return (q < qt && q0 + q < total) ? q0 + q : -1;
+        });
+        gather_features(X, RS, 64 + C, p.cv1, 64, RS, [&](int r) -> long long {
+            const int q = r / K;
+            if (q >= qt || nbr[r] < 0) return -1;
+            return (long long)((q0 + q) / nq) * cells + nbr[r];
+        });
+    }
+    __syncthreads();
+
+    dense<NB, 64, true>(ws, Y, 10, X);              // sum_xyz_encoding -> X[0:64]
+    dense<NB, 128, true>(ws, X, 128 + C, A);        // sum_cost_volume_0 on [enc, f1, stage-1 of neighbour]
+    dense<NB, 64, true>(ws, A, 128, Cb);            // sum_cost_volume_1 -> attention logits
+
+    // weights applied to the gathered stage-1 features, which sit at channel 64 + C (any alignment:
+    // softmax_pool indexes through act_index with absolute channels)
+    for (int t = threadIdx.x; t < p.qt * 64; t += blockDim.x) {
+        const int q = t >> 6, c = t & 63;
+        const long long gq = q0 + q;
+        if (gq >= p.total_q) break;
+        const int* nrow = nbr + q * g.K;
+        float m = -INFINITY;
+        for (int k = 0; k < g.K; ++k)
+            m = fmaxf(m, nrow[k] >= 0 ? Cb[act_index(c, q * g.K + k, RS)] : -1e10f);
+        float s = 0.f, acc = 0.f;
+        for (int k = 0; k < g.K; ++k) {
+            const float l = nrow[k] >= 0 ? Cb[act_index(c, q * g.K + k, RS)] : -1e10f;
+            const float e = expf(l - m);
+            s += e;
+            acc = fmaf(e, X[act_index(64 + C + c, q * g.K + k, RS)], acc);
+        }
+        p.out[gq * 64 + c] = acc / s;
+    }
+    if (p.dbg_nbr != nullptr)
+        for (int t = threadIdx.x; t < p.qt * g.K; t += blockDim.x)
+            if (q0 + t / g.K < p.total_q) p.dbg_nbr[q0 * g.K + t] = nbr[t];
+}
+
+// ================================================================================================
+// row_mlp: per-point MLP chains on concatenated (rows, C_i) tensors; up to two phases, the second
+// may take the first's output as one of its sources (set-upconv's second half feeding a predictor).
+struct RowMlpParams {
+    long long rows;
+    int rt;                    // rows per tile
+    int nphase;
+    int nsrc[2];
+    int src_c[2][3];           // channels of each source
+    int src_prev[2][3];        // 1: the source is the previous phase's output (kept in shared memory)
+    int nl[2], cout[2][3];
+    int total_chunks;
+    const float* src[2][2][3]; // [set][phase][i]
+    const float* weights[2];
+    float* out[2];
+    float* out_phase0[2];      // optional: also store phase 0's result (rows, cout) -- may be null
+};
+
+template <int NB>
+__global__ void __launch_bounds__(CTA_THREADS, 1) row_mlp_kernel(const RowMlpParams p)
+{
+    constexpr int RS = NB * 64;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    SmemCarver sc(smem_raw);
+    float* ring = sc.take<float>(RING * CHUNK_FLOATS);
+    uint64_t* bars = sc.take<uint64_t>(RING);
+    int xmax = 0;
+    for (int ph = 0; ph < p.nphase; ++ph) {
+        int c = 0;
+        for (int i = 0; i < p.nsrc[ph]; ++i) c += p.src_c[ph][i];
+        xmax = max(xmax, c);
+    }
+    float* X = sc.take<float>((size_t)((xmax + 3) & ~3) * RS);
+    float* A = sc.take<float>(128 * RS);
+    float* Bf = sc.take<float>(128 * RS);
+
+    const int set = blockIdx.y;
+    WeightStream ws;
+    ws.start(p.weights[set], ring, bars, p.total_chunks, 1);
+    const long long r0 = (long long)blockIdx.x * p.rt;
+    const long long rows = p.rows;
+    const int rt = p.rt;
+
+    const float* prev = nullptr;
+    int prev_c = 0;
+    for (int ph = 0; ph < p.nphase; ++ph) {
+        int c0 = 0;
+        for (int i = 0; i < p.nsrc[ph]; ++i) {
+            const int Ci = p.src_c[ph][i];
+            if (p.src_prev[ph][i]) {
+                for (int t = threadIdx.x; t < RS * prev_c; t += blockDim.x) {
+                    const int c = t / RS, r = t - c * RS;
+                    X[act_index(c0 + c, r, RS)] = prev[act_index(c, r, RS)];
+                }
+            } else {
+                gather_features(X, RS, c0, p.src[set][ph][i], Ci, RS, [&](int r) -> long long {
+                    return (r < rt && r0 + r < rows) ? r0 + r : -1;
+                });
+            }
+            c0 += Ci;
+        }
+        __syncthreads();
+        const float* in = X;
+        int cin = c0;
+        for (int l = 0; l < p.nl[ph]; ++l) {
+            float* o = (l & 1) ? Bf : A;
+            dense_rt<NB>(ws, in, cin, o, p.cout[ph][l]);
+            in = o;
+            cin = p.cout[ph][l];
+        }
+        prev = in;
+        prev_c = cin;
+        float* dst = (ph == p.nphase - 1) ? p.out[set] : p.out_phase0[set];
+        if (dst != nullptr)
+            for (int t = threadIdx.x; t < rt * cin; t += blockDim.x) {
+                const int r = t / cin, c = t - r * cin;
+                if (r0 + r >= rows) break;
+                dst[(r0 + r) * cin + c] = in[act_index(c, r, RS)];
+            }
+        // the next phase's gather overwrites X only; `prev` (A or Bf) stays valid because the
+        // first layer of the next phase writes A only after reading X... unless prev == A:
+        // copy-out above happens before any write, and the prev->X copy is fenced by the
+        // __syncthreads() before the dense chain.
+    }
+}
+
+// ================================================================================================
+// host side
+struct TileChoice { int nb, per_tile, tiles; };
+
+// Pick rows-per-tile (64 or 128) and a balanced split: `units` work items of `rows_per_unit` rows each.
+template <typename SmemFn>
+static TileChoice choose_tile(long long units, int rows_per_unit, int nsets, SmemFn smem_bytes)
+{
+    const int sms = device_info().sm_count;
+    TileChoice best{0, 0, 0};
+    double best_cost = 1e30;
+    for (int nb = 1; nb <= 2; ++nb) {
+        if (smem_bytes(nb) > (size_t)SMEM_LIMIT) continue;
+        const int cap = (64 * nb) / rows_per_unit;
+        if (cap < 1) continue;
+        long long tiles = (units + cap - 1) / cap;
+        const long long waves = (tiles * nsets + sms - 1) / sms;
+        // one 128-row tile costs ~1.7x a 64-row tile (weights and barriers are amortised over more rows)
+        const double cost = (double)waves * (nb == 1 ? 1.0 : 1.7);
+        if (cost < best_cost) {
+            best_cost = cost;
+            // spread the units evenly over as many tiles as the chosen number of waves can hold
+            long long slots = waves * sms / nsets;
+            if (slots < tiles) slots = tiles;
+            if (slots > units) slots = units;
+            int per = (int)((units + slots - 1) / slots);
+            if (per > cap) per = cap;
+            best = TileChoice{nb, per, (int)((units + per - 1) / per)};
+        }
+    }
+    return best;
+}
+
+template <typename Kernel>
+static int set_smem(Kernel k, size_t bytes, const char* what)
+{
+    cudaError_t err = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (err != cudaSuccess) return set_cuda_error(err, what);
+    return 0;
+}
+
+static size_t align16(size_t b) { return (b + 15) & ~size_t(15); }
+
+static size_t common_smem(int kt, int rs)
+{
+    return align16(RING_BYTES) + align16(RING * 8) + align16((size_t)kt * 8) + align16((size_t)rs * 4) +
+           align16((size_t)rs * 16);
+}
+
+static int check_window(const elo_window* w, const char* who)
+{
+    if (w->kernel_size_H <= 0 || w->kernel_size_W <= 0 || w->K <= 0 || !(w->distance > 0) || w->stride_h <= 0 ||
+        w->stride_w <= 0 || w->small_h <= 0 || w->small_w <= 0 || w->random_hw == nullptr)
+        return set_error(ELO_ERR_INVALID_ARGUMENT, who);
+    if ((long long)w->kernel_size_H * w->kernel_size_W > 5000)
+        return set_error(ELO_ERR_UNSUPPORTED, "window larger than 5000 cells");
+    if (w->small_h >= 32768 || w->small_w >= 32768) return set_error(ELO_ERR_UNSUPPORTED, "grid extent > 32767");
+    return 0;
+}
+
+static Window make_window(const elo_window* w)
+{
+    Window g;
+    g.h2 = w->small_h; g.w2 = w->small_w; g.kH = w->kernel_size_H; g.kW = w->kernel_size_W;
+    g.kt = w->kernel_size_H * w->kernel_size_W; g.stride_h = w->stride_h; g.stride_w = w->stride_w;
+    g.K = w->K; g.flag_copy = 0; g.d2max = w->distance * w->distance;
+    return g;
+}
+
+static QuerySet make_queries(const elo_queries* q)
+{
+    QuerySet s;
+    s.H1 = q->H; s.W1 = q->W; s.oh = q->out_h; s.ow = q->out_w; s.qs_h = q->q_stride_h; s.qs_w = q->q_stride_w;
+    return s;
+}
+
+static int check_queries(const elo_queries* q, const char* who)
+{
+    if (q->H <= 0 || q->W <= 0 || q->out_h <= 0 || q->out_w <= 0 || q->q_stride_h <= 0 || q->q_stride_w <= 0 ||
+        (q->out_h - 1) * q->q_stride_h >= q->H || (q->out_w - 1) * q->q_stride_w >= q->W)
+        return set_error(ELO_ERR_INVALID_ARGUMENT, who);
+    return 0;
+}
+
+static int width_ok(int c) { return c == 64 || c == 128; }
+
+}  // namespace elo
+
+using namespace elo;
+
+extern "C" int elo_group_mlp_max(const elo_group_mlp_desc* d, void* stream)
+{
+    if (d == nullptr) return set_error(ELO_ERR_INVALID_ARGUMENT, "group_mlp_max: null descriptor");
+    int rc = check_window(&d->window[0], "group_mlp_max: bad window");
+    if (rc) return rc;
+    rc = check_queries(&d->queries, "group_mlp_max: bad query grid");
+    if (rc) return rc;
+    if (d->batch_size < 0 || d->nsets < 1 || d->nsets > 2 || d->num_layers < 1 || d->num_layers > 3 ||
+        d->feat_channels <= 0 || (d->feat_channels & 3) || !d->xyz1 || !d->xyz2)
+        return set_error(ELO_ERR_INVALID_ARGUMENT, "group_mlp_max: bad arguments");
+    for (int l = 0; l < d->num_layers; ++l)
+        if (!width_ok(d->cout[l])) return set_error(ELO_ERR_UNSUPPORTED, "group_mlp_max: layer widths must be 64 or 128");
+    if (d->window[0].K > 64) return set_error(ELO_ERR_UNSUPPORTED, "group_mlp_max: K > 64");
+    if (d->batch_size == 0) return ELO_OK;
+
+    GroupMlpParams p;
+    p.qs = make_queries(&d->queries);
+    p.g = make_window(&d->window[0]);
+    const long long per_set = (long long)d->batch_size * p.qs.oh * p.qs.ow;
+    p.Cf = d->feat_channels;
+    p.nl = d->num_layers;
+    int cin = 3 + p.Cf, chunks = 0;
+    for (int l = 0; l < 3; ++l) {
+        p.cout[l] = l < p.nl ? d->cout[l] : 0;
+        if (l < p.nl) { chunks += layer_chunks(cin, p.cout[l]); cin = p.cout[l]; }
+    }
+    p.total_chunks = chunks;
+    p.xyz1 = d->xyz1; p.xyz2 = d->xyz2;
+    for (int s = 0; s < 2; ++s) {
+        const int u = s < d->nsets ? s : 0;
+        if (!d->feat2[u] || !d->weights[u] || !d->out[u] || !d->window[u].random_hw)
+            return set_error(ELO_ERR_INVALID_ARGUMENT, "group_mlp_max: null pointer");
+        p.feat2[s] = d->feat2[u]; p.random_hw[s] = d->window[u].random_hw; p.weights[s] = d->weights[u];
+        p.out[s] = d->out[u]; p.dbg_nbr[s] = d->dbg_nbr[u];
+        if (d->set_batch_offset[u] < 0) return set_error(ELO_ERR_INVALID_ARGUMENT, "group_mlp_max: negative batch offset");
+        p.q_base[s] = (long long)d->set_batch_offset[u] * p.qs.oh * p.qs.ow;
+        p.q_end[s] = p.q_base[s] + per_set;
+    }
+    const int kt = p.g.kt, xch = (3 + p.Cf + 3) & ~3;
+    auto smem = [&](int nb) { return common_smem(kt, 64 * nb) + (size_t)(xch + 256) * 64 * nb * 4; };
+    const TileChoice tc = choose_tile(per_set, p.g.K, d->nsets, smem);
+    if (tc.nb == 0) return set_error(ELO_ERR_UNSUPPORTED, "group_mlp_max: tile does not fit shared memory");
+    p.qt = tc.per_tile;
+    dim3 grid(tc.tiles, d->nsets);
+    const size_t bytes = smem(tc.nb);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (tc.nb == 1) {
+        if ((rc = set_smem(group_mlp_max_kernel<1>, bytes, "group_mlp_max smem"))) return rc;
+        group_mlp_max_kernel<1><<<grid, CTA_THREADS, bytes, st>>>(p);
+    } else {
+        if ((rc = set_smem(group_mlp_max_kernel<2>, bytes, "group_mlp_max smem"))) return rc;
+        group_mlp_max_kernel<2><<<grid, CTA_THREADS, bytes, st>>>(p);
+    }
+    cudaError_t err = cudaGetLastError();
+    return err == cudaSuccess ? ELO_OK : set_cuda_error(err, "group_mlp_max launch");
+}
+
+extern "C" int elo_cost_volume_1(const elo_cost_volume_desc* d, void* stream)
+{
+    if (d == nullptr) return set_error(ELO_ERR_INVALID_ARGUMENT, "cost_volume_1: null descriptor");
+    int rc = check_window(&d->window_q, "cost_volume_1: bad window");
+    if (rc) return rc;
+    if (d->batch_size < 0 || d->H <= 0 || d->W <= 0 || d->C <= 0 || (d->C & 3) || !d->xyz1 || !d->xyz2 || !d->f1 ||
+        !d->f2 || !d->weights_1 || !d->stage1_out || d->window_q.small_h != d->H || d->window_q.small_w != d->W ||
+        d->window_q.stride_h != 1 || d->window_q.stride_w != 1)
+        return set_error(ELO_ERR_INVALID_ARGUMENT, "cost_volume_1: bad arguments");
+    if (d->window_q.K > 64) return set_error(ELO_ERR_UNSUPPORTED, "cost_volume_1: nsample_q > 64");
+    if (d->batch_size == 0) return ELO_OK;
+    Cv1Params p;
+    p.qs.H1 = d->H; p.qs.W1 = d->W; p.qs.oh = d->H; p.qs.ow = d->W; p.qs.qs_h = 1; p.qs.qs_w = 1;
+    p.g = make_window(&d->window_q);
+    p.total_q = (long long)d->batch_size * d->H * d->W;
+    p.C = d->C;
+    const int xc = 10 + 2 * d->C;
+    p.total_chunks = layer_chunks(xc, 128) + layer_chunks(128, 64) + layer_chunks(64, 64) + layer_chunks(10, 64) +
+                     layer_chunks(128, 128) + layer_chunks(128, 64);
+    p.xyz1 = d->xyz1; p.xyz2 = d->xyz2; p.f1 = d->f1; p.f2 = d->f2; p.random_hw = d->window_q.random_hw;
+    p.weights = d->weights_1; p.out = d->stage1_out; p.dbg_nbr = d->dbg_nbr_q;
+    const int kt = p.g.kt, xch = (xc + 3) & ~3;
+    auto smem = [&](int nb) {
+        // the select-K scratch (8 warps x kt x 8 B) must fit in the A|Bf|Cb region it aliases
+        if ((size_t)kt * 64 > (size_t)320 * 64 * nb * 4) return (size_t)1 << 30;
+        return common_smem(kt, 64 * nb) + (size_t)(xch + 320) * 64 * nb * 4;
+    };
+    const TileChoice tc = choose_tile(p.total_q, p.g.K, 1, smem);
+    if (tc.nb == 0) return set_error(ELO_ERR_UNSUPPORTED, "cost_volume_1: tile does not fit shared memory");
+    p.qt = tc.per_tile;
+    const size_t bytes = smem(tc.nb);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (tc.nb == 1) {
+        if ((rc = set_smem(cost_volume_1_kernel<1>, bytes, "cost_volume_1 smem"))) return rc;
+        cost_volume_1_kernel<1><<<tc.tiles, CTA_THREADS, bytes, st>>>(p);
+    } else {
+        if ((rc = set_smem(cost_volume_1_kernel<2>, bytes, "cost_volume_1 smem"))) return rc;
+        cost_volume_1_kernel<2><<<tc.tiles, CTA_THREADS, bytes, st>>>(p);
+    }
+    cudaError_t err = cudaGetLastError();
+    return err == cudaSuccess ? ELO_OK : set_cuda_error(err, "cost_volume_1 launch");
+}
+
+extern "C" int elo_cost_volume_2(const elo_cost_volume_desc* d, void* stream)
+{
+    if (d == nullptr) return set_error(ELO_ERR_INVALID_ARGUMENT, "cost_volume_2: null descriptor");
+    int rc = check_window(&d->window_p, "cost_volume_2: bad window");
+    if (rc) return rc;
+    if (d->batch_size < 0 || d->H <= 0 || d->W <= 0 || d->C <= 0 || (d->C & 3) || !d->xyz1 || !d->f1 ||
+        !d->weights_2 || !d->stage1_out || !d->out || d->window_p.small_h != d->H || d->window_p.small_w != d->W ||
+        d->window_p.stride_h != 1 || d->window_p.stride_w != 1)
+        return set_error(ELO_ERR_INVALID_ARGUMENT, "cost_volume_2: bad arguments");
+    if (d->window_p.K > 64) return set_error(ELO_ERR_UNSUPPORTED, "cost_volume_2: nsample > 64");
+    if (d->batch_size == 0) return ELO_OK;
+    Cv2Params p;
+    p.qs.H1 = d->H; p.qs.W1 = d->W; p.qs.oh = d->H; p.qs.ow = d->W; p.qs.qs_h = 1; p.qs.qs_w = 1;
+    p.g = make_window(&d->window_p);
+    p.total_q = (long long)d->batch_size * d->H * d->W;
+    p.C = d->C;
+    p.total_chunks = layer_chunks(10, 64) + layer_chunks(128 + d->C, 128) + layer_chunks(128, 64);
+    p.xyz1 = d->xyz1; p.f1 = d->f1; p.cv1 = d->stage1_out; p.random_hw = d->window_p.random_hw;
+    p.weights = d->weights_2; p.out = d->out; p.dbg_nbr = d->dbg_nbr_p;
+    const int kt = p.g.kt;
+    auto smem = [&](int nb) { return common_smem(kt, 64 * nb) + (size_t)(12 + 128 + d->C + 192) * 64 * nb * 4; };
+    const TileChoice tc = choose_tile(p.total_q, p.g.K, 1, smem);
+    if (tc.nb == 0) return set_error(ELO_ERR_UNSUPPORTED, "cost_volume_2: tile does not fit shared memory");
+    p.qt = tc.per_tile;
+    const size_t bytes = smem(tc.nb);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (tc.nb == 1) {
+        if ((rc = set_smem(cost_volume_2_kernel<1>, bytes, "cost_volume_2 smem"))) return rc;
+        cost_volume_2_kernel<1><<<tc.tiles, CTA_THREADS, bytes, st>>>(p);
+    } else {
+        if ((rc = set_smem(cost_volume_2_kernel<2>, bytes, "cost_volume_2 smem"))) return rc;
+        cost_volume_2_kernel<2><<<tc.tiles, CTA_THREADS, bytes, st>>>(p);
+    }
+    cudaError_t err = cudaGetLastError();
+    return err == cudaSuccess ? ELO_OK : set_cuda_error(err, "cost_volume_2 launch");
+}
+
+extern "C" int elo_row_mlp(const elo_row_mlp_desc* d, void* stream)
+{
+    if (d == nullptr) return set_error(ELO_ERR_INVALID_ARGUMENT, "row_mlp: null descriptor");
+    if (d->rows < 0 || d->nsets < 1 || d->nsets > 2 || d->num_phases < 1 || d->num_phases > 2)
+        return set_error(ELO_ERR_INVALID_ARGUMENT, "row_mlp: bad arguments");
+    if (d->rows == 0) return ELO_OK;
+    RowMlpParams p;
+    p.rows = d->rows;
+    p.nphase = d->num_phases;
+    int chunks = 0, xmax = 0, prev_c = 0;
+    for (int ph = 0; ph < 2; ++ph) {
+        p.nsrc[ph] = 0; p.nl[ph] = 0;
+        for (int i = 0; i < 3; ++i) { p.src_c[ph][i] = 0; p.src_prev[ph][i] = 0; p.cout[ph][i] = 0; }
+        if (ph >= d->num_phases) continue;
+        const elo_row_mlp_phase* f = &d->phase[ph];
+        if (f->num_sources < 1 || f->num_sources > 3 || f->num_layers < 1 || f->num_layers > 3)
+            return set_error(ELO_ERR_INVALID_ARGUMENT, "row_mlp: bad phase");
+        p.nsrc[ph] = f->num_sources; p.nl[ph] = f->num_layers;
+        int cin = 0;
+        for (int i = 0; i < f->num_sources; ++i) {
+            p.src_c[ph][i] = f->channels[i];
+            p.src_prev[ph][i] = f->from_previous[i] ? 1 : 0;
+            if (f->channels[i] <= 0 || (f->channels[i] & 3)) return set_error(ELO_ERR_INVALID_ARGUMENT, "row_mlp: channels must be a positive multiple of 4");
+            if (f->from_previous[i] && (ph == 0 || f->channels[i] != prev_c))
+                return set_error(ELO_ERR_INVALID_ARGUMENT, "row_mlp: from_previous mismatch");
+            cin += f->channels[i];
+        }
+        xmax = cin > xmax ? cin : xmax;
+        for (int l = 0; l < f->num_layers; ++l) {
+            if (!width_ok(f->cout[l])) return set_error(ELO_ERR_UNSUPPORTED, "row_mlp: layer widths must be 64 or 128");
+            p.cout[ph][l] = f->cout[l];
+            chunks += layer_chunks(cin, f->cout[l]);
+            cin = f->cout[l];
+        }
+        prev_c = cin;
+    }
+    p.total_chunks = chunks;
+    for (int s = 0; s < 2; ++s) {
+        const int u = s < d->nsets ? s : 0;
+        if (!d->weights[u] || !d->out[u]) return set_error(ELO_ERR_INVALID_ARGUMENT, "row_mlp: null pointer");
+        p.weights[s] = d->weights[u]; p.out[s] = d->out[u]; p.out_phase0[s] = d->out_phase0[u];
+        for (int ph = 0; ph < 2; ++ph)
+            for (int i = 0; i < 3; ++i) {
+                p.src[s][ph][i] = (ph < d->num_phases && i < d->phase[ph].num_sources) ? d->phase[ph].src[u][i] : nullptr;
+                if (ph < d->num_phases && i < d->phase[ph].num_sources && !d->phase[ph].from_previous[i] && !p.src[s][ph][i])
+                    return set_error(ELO_ERR_INVALID_ARGUMENT, "row_mlp: null source");
+            }
+    }
+    const int xch = (xmax + 3) & ~3;
+    auto smem = [&](int nb) { return align16(RING_BYTES) + align16(RING * 8) + (size_t)(xch + 256) * 64 * nb * 4; };
+    const TileChoice tc = choose_tile(p.rows, 1, d->nsets, smem);
+    if (tc.nb == 0) return set_error(ELO_ERR_UNSUPPORTED, "row_mlp: tile does not fit shared memory");
+    p.rt = tc.per_tile;
+    dim3 grid(tc.tiles, d->nsets);
+    const size_t bytes = smem(tc.nb);
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc;
+    if (tc.nb == 1) {
+        if ((rc = set_smem(row_mlp_kernel<1>, bytes, "row_mlp smem"))) return rc;
+        row_mlp_kernel<1><<<grid, CTA_THREADS, bytes, st>>>(p);
+    } else {
+        if ((rc = set_smem(row_mlp_kernel<2>, bytes, "row_mlp smem"))) return rc;
+        row_mlp_kernel<2><<<grid, CTA_THREADS, bytes, st>>>(p);
+    }
+    cudaError_t err = cudaGetLastError();
+    return err == cudaSuccess ? ELO_OK : set_cuda_error(err, "row_mlp launch");
+}

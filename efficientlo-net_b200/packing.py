@@ -1,0 +1,34 @@
+"""Host-side packing of folded weights into the layouts the kernels stream (csrc/elo_mlp.cuh)."""
+import torch
+
+from .params import fold_bn
+
+CHUNK_FLOATS = 2048
+
+
+def pack_stream(P, scopes):
+    """Chunked stream for the shared-memory GEMM engine: per layer, row 0 = folded bias, rows 1..Cin =
+    W'[k][:], zero rows up to a multiple of 2048 / Cout; layers back to back in execution order."""
+    parts = []
+    for scope in scopes:
+        w, b = fold_bn(P, scope)
+        cin, cout = w.shape
+        if cout not in (64, 128):
+            raise ValueError("%s: the GEMM engine takes 64- or 128-wide layers, got %d" % (scope, cout))
+        rows_per_chunk = CHUNK_FLOATS // cout
+        rows = cin + 1
+        padded = (rows + rows_per_chunk - 1) // rows_per_chunk * rows_per_chunk
+        block = torch.zeros(padded, cout, dtype=torch.float32)
+        block[0] = b.float()
+        block[1:rows] = w.float()
+        parts.append(block.reshape(-1))
+    return torch.cat(parts).contiguous()
+
+
+def pack_plain(P, scopes):
+    """Plain packing for the register-MLP set-conv: W1, b1, W2, b2, W3, b3 (row-major [Cin][Cout])."""
+    parts = []
+    for scope in scopes:
+        w, b = fold_bn(P, scope)
+        parts += [w.float().reshape(-1), b.float().reshape(-1)]
+    return torch.cat(parts).contiguous()

@@ -1,0 +1,213 @@
+"""PWCLO-Net forward on B200 -- mirror of the reference's pwclo_model.py (placeholder_inputs :19,
+get_model :30-433, get_loss :437-481).
+
+get_model takes the reference's arguments and returns its 11-tuple.  The wiring follows the reference
+block for block (the comments cite its lines); what differs is the execution: ~40 fused sm_100a kernel
+launches per forward instead of several thousand TensorFlow ops, both frames of the siamese pyramid and
+both up-convs / predictors of a level sharing launches, the pose warp fused into the re-projection, and
+the pose composition into the attention-pooling kernel.  Nothing here synchronises with the host, so a
+whole forward can be captured in a CUDA graph (engine.py).
+"""
+import math
+
+import torch
+
+from . import model_util as mu
+from . import pointnet_util as pu
+from .params import make_perms
+from .store import ParamStore, current_store, use_store
+
+# hyper-parameters, literals of pwclo_model.py:38-43 and of the call sites
+DOWN_CONV_DIS = [0.5, 3.0, 6.0, 12.0]
+UP_CONV_DIS = [3.0, 6.0, 9.0]
+COST_VOLUME_DIS = [1.0, 2.0, 4.0]
+STRIDE_H = [1, 1, 4, 2, 2, 1]
+STRIDE_W = [1, 1, 8, 2, 2, 2]
+DOWN_CFG = [(32, (9, 15)), (32, (7, 11)), (16, (5, 9)), (16, (5, 9))]     # (K_sample, kernel_size) layer0..3
+CV_KERNEL_Q = {2: (5, 15), 1: (7, 25), 0: (11, 41)}
+
+
+def placeholder_inputs(batch_size, NUM_POINTS, device="cuda"):
+    """Zero tensors with the shapes of the reference's placeholders (pwclo_model.py:19-27)."""
+    eye = torch.eye(4, device=device).expand(batch_size, 4, 4).contiguous()
+    return (torch.zeros(batch_size, NUM_POINTS * 2, 6, device=device), eye.clone(), eye.clone(), eye.clone())
+
+
+def pyramid_shapes(H_input, W_input):
+    """out_h_list / out_w_list of pwclo_model.py:45-50."""
+    oh, ow = [math.ceil(H_input / STRIDE_H[0])], [math.ceil(W_input / STRIDE_W[0])]
+    for i in range(1, 6):
+        oh.append(math.ceil(oh[-1] / STRIDE_H[i]))
+        ow.append(math.ceil(ow[-1] / STRIDE_W[i]))
+    return oh, ow
+
+
+def _heads(store, lvl):
+    suffix = "coarse" if lvl == 3 else "det"
+    names = ["l%d_big" % lvl, "l%d_q_%s" % (lvl, suffix), "l%d_t_%s" % (lvl, suffix)]
+    out = []
+    for n in names:
+        out += [store.tensor(n + "/weights"), store.tensor(n + "/biases")]
+    return tuple(out)
+
+
+def get_model(point_cloud, H_input, W_input, T_gt, T_trans, T_trans_inv, is_training, bn_decay=None,
+              params=None, perms=None, aug_frame=None, keep=None):
+    """Whole network (pwclo_model.py:30-433).
+
+    point_cloud (B, 2*N, 6) fp32 on the GPU, frame 1 in rows [0,N), frame 2 in [N,2N), xyz in channels
+    0:3; T_gt / T_trans / T_trans_inv (B,4,4).  ``params``: a ParamStore or a flat parameter dict
+    (params.py); ``perms``: scan orders per call site (params.make_perms) -- the reference redraws them
+    every run; ``aug_frame``: which frame each sample augments (the reference draws it with numpy at
+    graph-build time, :59; default 2).  ``keep``: optional dict that receives named intermediates.
+    Returns (l0_q, l0_t, l1_q, l1_t, l2_q, l2_t, l3_q, l3_t, l0_xyz_f1, q_gt, t_gt)."""
+    pu._check_training(is_training)
+    store = params if isinstance(params, ParamStore) else (ParamStore(params, point_cloud.device) if params is not None
+                                                           else current_store())
+    if perms is None:
+        perms = make_perms(int(torch.randint(0, 2 ** 31 - 1, (1,))))
+    B = point_cloud.shape[0]
+    N = point_cloud.shape[1] // 2
+    dev = point_cloud.device
+    if point_cloud.dtype != torch.float32 or not point_cloud.is_contiguous():
+        point_cloud = point_cloud.float().contiguous()
+    oh, ow = pyramid_shapes(H_input, W_input)
+    K = keep if keep is not None else {}
+    want = keep is not None
+    if aug_frame is None:
+        aug_frame = [2] * B
+
+    with use_store(store):
+        # ---- PreProcess (:61) + ProjectPC2SphericalRing x2 (:63-64), both frames in one pass.
+        # Samples are stacked frame-major: s = f*B + b reads point_cloud[b, f*N:(f+1)*N, 0:3] in place.
+        eye = store.eye(B)
+        T_gt = T_gt.to(dev) if T_gt is not None else eye
+        q_gt, t_gt = mu.gt_pose(T_gt, eye if T_trans is None else T_trans.to(dev),
+                                eye if T_trans_inv is None else T_trans_inv.to(dev), aug_frame)
+        T_aug = None
+        if not _all_identity(T_trans):
+            T_aug = torch.cat([mu.aug_matrices(T_trans, aug_frame, 1, B, dev),
+                               mu.aug_matrices(T_trans, aug_frame, 2, B, dev)], 0)
+        stride_pt, stride_b = point_cloud.stride(1), point_cloud.stride(0)
+        xyz_in, _, _ = mu.project_points(point_cloud[:, :N, 0:3], None, H_input, W_input, mode=1, T=T_aug,
+                                         inner_batch=B, outer_stride=N * stride_pt, batch_size=2 * B)
+        if want:
+            K["xyz_f1_proj"], K["xyz_f2_proj"] = xyz_in[:B], xyz_in[B:]
+
+        # ---- strided xyz pyramid (:88-114): pure slicing of the range image
+        xyz = [None] * 4
+        cur = xyz_in[:, ::STRIDE_H[1], ::STRIDE_W[1]]
+        for l in range(4):
+            cur = cur[:, ::STRIDE_H[l + 2], ::STRIDE_W[l + 2]][:, :oh[l + 2], :ow[l + 2]].contiguous()
+            xyz[l] = cur                                                        # (2B, oh, ow, 3)
+
+        # ---- siamese feature pyramid (:117-165): frames share weights, each call its own scan order
+        pts = [None] * 4
+        src_xyz, src_pts, src_c = xyz_in, None, 3
+        for l in range(4):
+            sel = pu.SelectedIdx(B, STRIDE_H[l + 2] * (STRIDE_H[1] if l == 0 else 1),
+                                 STRIDE_W[l + 2] * (STRIDE_W[1] if l == 0 else 1), oh[l + 2], ow[l + 2], dev)
+            scopes = ["sa1/layer%d/conv%d" % (l, j) for j in range(3)]
+            feat = pu.set_conv(src_xyz, src_pts, sel, DOWN_CFG[l][0], DOWN_CFG[l][1], DOWN_CONV_DIS[l], scopes, store,
+                               [perms["sa1/layer%d/f1" % l], perms["sa1/layer%d/f2" % l]], feat_channels=src_c,
+                               set_batch_offsets=(0, B))
+            pts[l] = feat                                                       # (2B, n_l, C_l)
+            src_xyz, src_pts, src_c = xyz[l], feat.view(2 * B, oh[l + 2], ow[l + 2], -1), feat.shape[-1]
+            if want:
+                K["l%d_points_f1" % l], K["l%d_points_f2" % l] = feat[:B], feat[B:]
+
+        def f1(t):
+            return t[:B]
+
+        def f2(t):
+            return t[B:]
+
+        def grid(l, t):
+            return t.reshape(t.shape[0], oh[l + 2], ow[l + 2], -1)
+
+        # ---- initial cost volume on level 2 and its set-conv to level 3 (:170-178)
+        l2_new = pu.cost_volume(f1(xyz[2]), f2(xyz[2]), grid(2, f1(pts[2])), grid(2, f2(pts[2])), [3, 5], [5, 35],
+                                4, 32, COST_VOLUME_DIS[2], [128, 64, 64], [128, 64], False, bn_decay,
+                                "flow_embedding_l2_origin", random_hw_q=perms["flow_embedding_l2_origin/q"],
+                                random_hw_p=perms["flow_embedding_l2_origin/p"])
+        sel3 = pu.SelectedIdx(B, STRIDE_H[5], STRIDE_W[5], oh[5], ow[5], dev)
+        l3_cv = pu.set_conv(f1(xyz[2]), grid(2, l2_new), sel3, 16, (5, 9), DOWN_CONV_DIS[3],
+                            ["new_layer3/conv%d" % j for j in range(3)], store, [perms["new_layer3"]])
+        # ---- level 3: embedding mask, attention pooling, coarse pose (:181-208)
+        l3_w = pu.flow_predictor(f1(pts[3]), None, l3_cv, [128, 64], False, bn_decay, "l3_costvolume_predict_ww")
+        l3_xyz = f1(xyz[3]).reshape(B, -1, 3)
+        pose = mu.pose_head_call(l3_cv, l3_w, l3_xyz, heads=_heads(store, 3), want_pooled=want)
+        q, t = pose["q"], pose["t"]
+        q_norm, t_lvl = {3: pose["q_norm"]}, {3: t}
+        if want:
+            K.update(l2_points_f1_new=l2_new, l3_points_f1_cost_volume=l3_cv, l3_w=l3_w, l3_q=q, l3_t=t,
+                     l3_pooled=pose["pooled"])
+
+        up_xyz = f1(xyz[3])                 # level 2 up-samples from the UN-warped level-3 grid (:247)
+        up_w, up_pred = grid(3, l3_w), grid(3, l3_cv)
+        for lvl in (2, 1, 0):
+            h, w_ = oh[lvl + 2], ow[lvl + 2]
+            C = pts[lvl].shape[-1]
+            # warp with the coarse pose and re-project (:213-237): one fused pass
+            xyz_wp, pts_wp, warped = mu.project_points(f1(xyz[lvl]).reshape(B, -1, 3), f1(pts[lvl]), h, w_, mode=2,
+                                                       q=q, t=t, want_points=want)
+            # cost volume between the warped frame 1 and frame 2 (:242-244)
+            cv = pu.cost_volume(xyz_wp, f2(xyz[lvl]), pts_wp, grid(lvl, f2(pts[lvl])), [3, 5], CV_KERNEL_Q[lvl], 4, 6,
+                                COST_VOLUME_DIS[lvl], [128, 64, 64], [128, 64], False, bn_decay,
+                                "flow_embedding_l%d" % lvl, random_hw_q=perms["flow_embedding_l%d/q" % lvl],
+                                random_hw_p=perms["flow_embedding_l%d/p" % lvl])
+            # the two set-upconvs of the level (:247-251) share one launch for their first half ...
+            names = ["up_sa_layer_layer_l%dw" % lvl, "up_sa_layer_layer_l%dcostvolume" % lvl]
+            ups = pu.up_conv_group(xyz_wp, up_xyz, [up_w, up_pred], (7, 15), STRIDE_H[lvl + 3], STRIDE_W[lvl + 3], 8,
+                                   UP_CONV_DIS[lvl], [["%s/up_1_%d" % (n, j) for j in range(2)] for n in names],
+                                   store, [perms[n] for n in names])
+            # ... and one launch for their second half chained into the two predictors (:253-254)
+            rows = B * h * w_
+            pts_w = pts_wp.reshape(rows, C)
+            cv_r = cv.reshape(rows, 64)
+            pred_names = ["l%d_w_predict" % lvl, "l%d_costvolume_predict" % lvl]
+            streams = [store.stream(["%s/up_2_0" % n, "%s/up_2_1" % n, "%s/conv_predictor0" % p,
+                                     "%s/conv_predictor1" % p]) for n, p in zip(names, pred_names)]
+            phases = [dict(sources=[[u.reshape(rows, 64) for u in ups], [pts_w]], channels=[64, C], couts=[128, 64]),
+                      dict(sources=[[pts_w], None, [cv_r]], channels=[C, 64, 64], couts=[128, 64])]
+            outs, up2 = pu.row_mlp(rows, phases, streams, 64, dev, want_phase0=want, phase0_channels=64)
+            wgt, pred = outs[0].view(B, h * w_, 64), outs[1].view(B, h * w_, 64)
+            # attention pooling over the valid re-projected pixels + pose refinement (:262-280)
+            pose = mu.pose_head_call(pred, wgt, xyz_wp.reshape(B, -1, 3), heads=_heads(store, lvl), coarse=(q, t),
+                                     want_pooled=want)
+            if want:
+                K.update({"l%d_flow_warp" % lvl: warped, "l%d_xyz_warp_proj" % lvl: xyz_wp,
+                          "l%d_points_warp_proj" % lvl: pts_wp, "l%d_cost_volume" % lvl: cv,
+                          "l%d_w_up" % lvl: up2[0].view(B, h * w_, 64), "l%d_p_up" % lvl: up2[1].view(B, h * w_, 64),
+                          "l%d_predict" % lvl: pred, "l%d_w" % lvl: wgt, "l%d_pooled" % lvl: pose["pooled"],
+                          "l%d_q" % lvl: pose["q"], "l%d_t" % lvl: pose["t"]})
+            q, t = pose["q"], pose["t"]
+            q_norm[lvl], t_lvl[lvl] = pose["q_norm"], t
+            up_xyz, up_w, up_pred = xyz_wp, wgt.view(B, h, w_, 64), pred.view(B, h, w_, 64)
+
+    l0_xyz_f1 = f1(xyz[0]).reshape(B, -1, 3)
+    return (q_norm[0], t_lvl[0], q_norm[1], t_lvl[1], q_norm[2], t_lvl[2], q_norm[3], t_lvl[3], l0_xyz_f1,
+            q_gt, t_gt)
+
+
+def _all_identity(T):
+    """Host-known identity augmentation (inference, main.py:311-312) lets the projection skip the matmul.
+    Only CPU tensors are inspected: a device tensor would need a sync, so it is treated as non-identity."""
+    if T is None:
+        return True
+    if T.is_cuda:
+        return False
+    return bool(torch.equal(T, torch.eye(4).expand_as(T)))
+
+
+def get_loss(l0_q, l0_t, l1_q, l1_t, l2_q, l2_t, l3_q, l3_t, q_gt, t_gt, w_x, w_q):
+    """Multi-scale pose loss with learnable uncertainty weights (pwclo_model.py:437-481)."""
+    t_gt = t_gt.squeeze(-1)
+
+    def level(q, t):
+        qn = q / (torch.sqrt((q * q).sum(-1, keepdim=True) + 1e-10) + 1e-10)
+        lq = torch.sqrt(((q_gt - qn) * (q_gt - qn)).sum(-1, keepdim=True) + 1e-10).mean()
+        lx = torch.sqrt((t - t_gt) * (t - t_gt) + 1e-10).mean()
+        return lx * torch.exp(-w_x) + w_x + lq * torch.exp(-w_q) + w_q
+
+    return 1.6 * level(l3_q, l3_t) + 0.8 * level(l2_q, l2_t) + 0.4 * level(l1_q, l1_t) + 0.2 * level(l0_q, l0_t)

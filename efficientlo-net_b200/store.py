@@ -1,0 +1,98 @@
+"""Variable store: the reference's implicit tf.variable_scope / tf.get_variable lookup, made explicit.
+
+The blocks of pointnet_util.py take a ``scope`` string exactly like the reference's; the weights they
+need are looked up in the store that is current (``with use_store(store):``) under the enclosing
+``variable_scope`` prefixes, e.g. ``with variable_scope('sa1'): down_conv(..., scope='layer0')`` reads
+``sa1/layer0/conv0/weights`` etc. -- the names of the shipped checkpoint.
+Packed, BN-folded device copies are cached per (layer list, device).
+"""
+import contextlib
+
+import torch
+
+from . import packing
+
+_current = []
+_prefix = []
+
+
+class ParamStore:
+    def __init__(self, params, device="cuda"):
+        self.P = params
+        self.device = torch.device(device)
+        self._cache = {}
+
+    def stream(self, scopes):
+        key = ("stream",) + tuple(scopes)
+        if key not in self._cache:
+            self._cache[key] = packing.pack_stream(self.P, scopes).to(self.device)
+        return self._cache[key]
+
+    def plain(self, scopes):
+        key = ("plain",) + tuple(scopes)
+        if key not in self._cache:
+            self._cache[key] = packing.pack_plain(self.P, scopes).to(self.device)
+        return self._cache[key]
+
+    def tensor(self, name):
+        key = ("raw", name)
+        if key not in self._cache:
+            self._cache[key] = self.P[name].float().contiguous().to(self.device)
+        return self._cache[key]
+
+    def widths(self, scopes):
+        return [int(self.P[s + "/weights"].shape[1]) for s in scopes]
+
+    def cin(self, scope):
+        return int(self.P[scope + "/weights"].shape[0])
+
+    def scratch(self, name, shape, dtype, fill=None):
+        """Persistent scratch buffers (projection cell minima, pose-head partials, counters)."""
+        key = ("scratch", name, tuple(shape), dtype)
+        if key not in self._cache:
+            t = torch.empty(shape, dtype=dtype, device=self.device)
+            if fill is not None:
+                t.fill_(fill)
+            self._cache[key] = t
+        return self._cache[key]
+
+    def eye(self, batch):
+        """(batch, 4, 4) identity matrices on the device (constant)."""
+        key = ("eye", batch)
+        if key not in self._cache:
+            self._cache[key] = torch.eye(4, device=self.device).expand(batch, 4, 4).contiguous()
+        return self._cache[key]
+
+    def invalidate(self):
+        self._cache.clear()
+
+
+@contextlib.contextmanager
+def use_store(store):
+    _current.append(store)
+    try:
+        yield store
+    finally:
+        _current.pop()
+
+
+def current_store(explicit=None):
+    if explicit is not None:
+        return explicit
+    if not _current:
+        raise RuntimeError("no parameter store: wrap the call in `with use_store(ParamStore(params)):` "
+                           "or pass params=")
+    return _current[-1]
+
+
+@contextlib.contextmanager
+def variable_scope(name):
+    _prefix.append(name)
+    try:
+        yield
+    finally:
+        _prefix.pop()
+
+
+def scoped(name):
+    return "/".join(_prefix + [name])

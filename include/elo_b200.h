@@ -55,6 +55,153 @@ int elo_fused_conv_random_k(int batch_size, int H, int W, int npoints, int kerne
                             float *valid_in_dis_idx, float *selected_mask, int small_h, int small_w,
                             void *stream);
 
+
+/* ------------------------------------------------------------------------------------------------
+ * Fused blocks.  These have no single native counterpart in the reference: each replaces the chain
+ * of stock TensorFlow kernels that one Python block of utils/pointnet_util.py / model_util.py builds
+ * around the custom op (gather_nd, concat, 1x1 conv + bias + batch-norm + ReLU per layer, mask,
+ * reduce_max / softmax / reduce_sum).  Descriptors are plain C structs; tensors are fp32,
+ * C-contiguous, channel-last, on the device.
+ *
+ * Weights are the packed stream efficientlo-net_b200/packing.py produces: per layer, row 0 = bias
+ * with the inference batch-norm folded in, rows 1..Cin = W'[k][0..Cout), zero rows up to a multiple
+ * of (2048 / Cout); layers back to back in execution order.
+ */
+typedef struct {
+    int kernel_size_H, kernel_size_W, K;
+    float distance;
+    int stride_h, stride_w;   /* query (h,w) -> window centre (h/stride_h, w/stride_w) in the searched grid */
+    int small_h, small_w;     /* extent of the searched grid */
+    const int *random_hw;     /* (kernel_size_H*kernel_size_W) scan order */
+} elo_window;
+
+typedef struct {
+    int H, W;                    /* query image */
+    int out_h, out_w;            /* queries per sample: cells (i*q_stride_h, j*q_stride_w) */
+    int q_stride_h, q_stride_w;  /* 1,1 = every pixel (get_hw_idx); >1 = strided centres (get_selected_idx) */
+} elo_queries;
+
+/* set-conv (utils/pointnet_util.py:179-250 down_conv, mlp2 = None) and the first half of set-upconv
+ * (:254-298): random-K neighbours of each query in (xyz2, feat2); rows [q_k - p, feat2_k] -> 2..3
+ * layers (each 64 or 128 wide) -> * mask -> max over K -> out (B, out_h*out_w, cout[last]).
+ * nsets = 2 runs two parameter sets (feat2 / scan order / weights / out) over the same geometry in
+ * one launch -- the model's two up_conv calls per level (pwclo_model.py:247-251). */
+typedef struct {
+    int batch_size;           /* samples per parameter set */
+    elo_queries queries;
+    int nsets;
+    int set_batch_offset[2];  /* first sample of each set in the tensors (0,0 for the two up_conv calls;
+                                 0,B when the two frames of the siamese pyramid are stacked as (2B,...)) */
+    elo_window window[2];
+    int feat_channels;        /* channels of feat2, multiple of 4 */
+    int num_layers;
+    int cout[3];
+    const float *xyz1;        /* (B, H, W, 3) query image */
+    const float *xyz2;        /* (B, small_h, small_w, 3) searched grid */
+    const float *feat2[2];    /* (B, small_h, small_w, feat_channels) */
+    const float *weights[2];
+    float *out[2];
+    int *dbg_nbr[2];          /* optional (B, n, K): selected linear cell of the searched grid, -1 = masked */
+} elo_group_mlp_desc;
+int elo_group_mlp_max(const elo_group_mlp_desc *desc, void *stream);
+
+/* attentive cost volume (utils/pointnet_util.py:33-149), mlp1 = [128,64,64], mlp2 = [128,64].
+ * elo_cost_volume_1: select-K (window_q, distance as given -- the reference passes 1000) of frame 2
+ *   around each frame-1 pixel -> CV_0..2, CV_xyz, sum_CV_0..1 -> masked softmax over K -> stage1_out
+ *   (B, H*W, 64).
+ * elo_cost_volume_2: random-K (window_p) self-neighbours in frame 1 -> sum_xyz_encoding,
+ *   sum_cost_volume_0..1 -> masked softmax over K of the gathered stage-1 features -> out (B, H*W, 64).
+ * Stage 2 reads stage 1 at neighbouring pixels, hence two launches. */
+typedef struct {
+    int batch_size, H, W, C;  /* both frames are (B, H, W, .); C = feature channels, multiple of 4 */
+    elo_window window_q;      /* stage 1: kernel_size2, nsample_q */
+    elo_window window_p;      /* stage 2: kernel_size1, nsample, distance */
+    const float *xyz1, *xyz2; /* (B, H, W, 3) warped frame 1, frame 2 */
+    const float *f1, *f2;     /* (B, H, W, C) */
+    const float *weights_1, *weights_2;
+    float *stage1_out;        /* (B, H*W, 64) written by stage 1, read by stage 2 */
+    float *out;               /* (B, H*W, 64) */
+    int *dbg_nbr_q, *dbg_nbr_p;
+} elo_cost_volume_desc;
+int elo_cost_volume_1(const elo_cost_volume_desc *desc, void *stream);
+int elo_cost_volume_2(const elo_cost_volume_desc *desc, void *stream);
+
+/* per-point MLP chains on the concatenation of up to three (rows, C_i) tensors
+ * (utils/pointnet_util.py:153-175 flow_predictor; :303-311 the second half of up_conv).  A second
+ * phase may use the first phase's result as one of its sources without leaving the chip. */
+typedef struct {
+    int num_sources;
+    int channels[3];          /* multiples of 4 */
+    int from_previous[3];     /* 1: this source is the previous phase's output */
+    int num_layers;
+    int cout[3];              /* 64 or 128 */
+    const float *src[2][3];   /* [set][source], (rows, channels[i]) */
+} elo_row_mlp_phase;
+typedef struct {
+    long long rows;
+    int nsets;
+    int num_phases;
+    elo_row_mlp_phase phase[2];
+    const float *weights[2];
+    float *out[2];            /* (rows, cout of the last layer of the last phase) */
+    float *out_phase0[2];     /* optional: phase 0's result */
+} elo_row_mlp_desc;
+int elo_row_mlp(const elo_row_mlp_desc *desc, void *stream);
+
+/* set-conv for the narrow pyramid layers (pwclo_model.py:126-135), one warp per 32/K queries, MLP in
+ * registers.  Same descriptor as elo_group_mlp_max with nsets = 1, num_layers = 3, xyz2 == xyz1,
+ * feat2[0] may be NULL (all-zero input features, pwclo_model.py:69-70); supported (feat_channels;
+ * cout; K): (3; 8,8,16; 32), (16; 16,16,32; 32), (32; 32,32,64; 16).  weights[0] here is the PLAIN
+ * packing W1[(3+Cf)][c1], b1, W2[c1][c2], b2, W3[c2][c3], b3 (batch-norm folded).  nsets = 2 runs two
+ * sample ranges with their own scan orders (window[1].random_hw) but the same weights / tensors. */
+int elo_set_conv_small(const elo_group_mlp_desc *desc, void *stream);
+
+/* PreProcess / pose warp fused with ProjectPC2SphericalRing (model_util.py:181-292, 346-445;
+ * pwclo_model.py:213-232).  mode 0: project the points as they are; mode 1: 35 m crop, optional
+ * 4x4 augmentation T (B,4,4) (NULL = none), empty points stay empty; mode 2: p' = q p q^-1 + t with
+ * per-sample q (B,4) (w,x,y,z) and t (B,3), empty points stay empty.  Per cell the nearest point
+ * wins (equal ranges accumulate); out_xyz (B,H,W,3), out_feat (B,H,W,C) are fully written.
+ * points: sample b, point n at points + b*batch_stride + n*point_stride (floats) -- lets the kernel
+ * read xyz straight out of the reference's (B, 2N, 6) input.  cellmin: (B,H,W) uint32 scratch. */
+typedef struct {
+    int batch_size, num_points, H, W, C, mode;
+    const float *points;
+    long long point_stride, batch_stride;
+    int inner_batch;          /* 0: sample s at s*batch_stride.  >0: s = f*inner_batch + b lives at
+                                 b*batch_stride + f*outer_stride (frame-major view of a (B,2N,6) cloud) */
+    long long outer_stride;
+    const float *feat;        /* (B, num_points, C) or NULL */
+    const float *T, *q, *t;
+    float pi, az_res, v_res, v_off;   /* fp32 constants of model_util.py:204-210 */
+    unsigned *cellmin;
+    float *out_xyz, *out_feat;
+    float *out_points;        /* optional (B, num_points, 3): the transformed points */
+} elo_project_desc;
+int elo_project(const elo_project_desc *desc, void *stream);
+
+/* softmax_valid (model_util.py:319-343) + conv1d heads + pose composition (pwclo_model.py:194-208,
+ * 262-280).  feature / weight (B,N,64); xyz (B,N,3) marks valid points (not exactly zero).
+ * Outputs q_out (B,4) (composed, un-normalised as the next level consumes it), t_out (B,3),
+ * q_norm_out (B,4) (pwclo_model.py:427-430), pooled_out (B,64) optional.
+ * w_big == NULL: only the pooling (softmax_valid) is done and pooled_out is required.
+ * partial: (B, num_slices, 192) scratch; counter: (B) uint32, zero before the first call. */
+typedef struct {
+    int batch_size, num_points, num_slices, has_coarse;
+    const float *feature, *weight, *xyz;
+    const float *w_big, *b_big, *w_q, *b_q, *w_t, *b_t;
+    const float *q_coarse, *t_coarse;
+    float *partial;
+    unsigned *counter;
+    float *q_out, *t_out, *q_norm_out, *pooled_out;
+} elo_pose_head_desc;
+int elo_pose_head(const elo_pose_head_desc *desc, void *stream);
+
+/* Ground-truth pose as the network's (q, t) parametrisation (model_util.py:386-426): per sample
+ * T = T_trans T_gt (aug_frame 2) or T_gt T_trans_inv (aug_frame 1); q from the zyx Euler angles of R,
+ * t = T[:3,3].  T_* are (B,4,4) row-major, aug_frame (B) int32 (NULL = all 2); q_gt (B,4), t_gt (B,3). */
+int elo_gt_pose(int batch_size, const float *T_gt, const float *T_trans, const float *T_trans_inv,
+                const int *aug_frame, float *q_gt, float *t_gt, void *stream);
+
 #ifdef __cplusplus
 }
 #endif
