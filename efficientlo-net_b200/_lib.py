@@ -100,6 +100,8 @@ def lib():
         handle.elo_last_error.restype = ctypes.c_char_p
         handle.elo_last_error.argtypes = []
         handle.elo_version.restype = _c_int
+        handle.elo_launch_count.restype = _c_ll
+        handle.elo_launch_count.argtypes = []
         for name, argtypes in SIGNATURES.items():
             fn = getattr(handle, name)
             fn.argtypes = argtypes
@@ -127,11 +129,27 @@ def ptr(t):
     return None if t is None else t.data_ptr()
 
 
+# bench.py's per-kernel timing: when this is a list, every descriptor call is bracketed by CUDA events
+# on the launching stream and (name, tag, start, end) is appended.
+PROFILE = None
+PROFILE_TAG = [""]
+
+
+def launch_count():
+    return int(lib().elo_launch_count())
+
+
 def call(name, desc, device):
     """Launch one descriptor-style entry point on torch's current stream of `device`."""
     import torch
     with torch.cuda.device(device):
+        if PROFILE is not None:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(torch.cuda.current_stream(device))
         rc = getattr(lib(), name)(ctypes.byref(desc), stream_ptr(device))
+        if PROFILE is not None:
+            e1.record(torch.cuda.current_stream(device))
+            PROFILE.append((name, PROFILE_TAG[0], e0, e1))
     check(rc, name)
 
 

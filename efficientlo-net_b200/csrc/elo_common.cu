@@ -3,12 +3,17 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <atomic>
+
 #include "../../include/elo_b200.h"
 #include "elo_common.cuh"
 
 namespace elo {
 
 static thread_local char g_error[512] = "";
+static std::atomic<long long> g_launches{0};
+
+void count_launches(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
 int set_error(int code, const char* msg)
 {
@@ -46,3 +51,4 @@ const DeviceInfo& device_info()
 
 extern "C" const char* elo_last_error(void) { return elo::g_error; }
 extern "C" int elo_version(void) { return 100; }
+extern "C" long long elo_launch_count(void) { return elo::g_launches.load(std::memory_order_relaxed); }

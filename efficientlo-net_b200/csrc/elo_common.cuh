@@ -17,4 +17,7 @@ const DeviceInfo& device_info();
 int set_error(int code, const char* msg);
 int set_cuda_error(cudaError_t err, const char* where);
 
+// Every kernel launch of this library is counted (elo_launch_count() in the C ABI): bench.py reports it.
+void count_launches(int n);
+
 }  // namespace elo

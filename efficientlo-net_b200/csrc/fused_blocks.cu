@@ -588,6 +588,7 @@ extern "C" int elo_group_mlp_max(const elo_group_mlp_desc* d, void* stream)
         if ((rc = set_smem(group_mlp_max_kernel<2>, bytes, "group_mlp_max smem"))) return rc;
         group_mlp_max_kernel<2><<<grid, CTA_THREADS, bytes, st>>>(p);
     }
+    count_launches(1);
     cudaError_t err = cudaGetLastError();
     return err == cudaSuccess ? ELO_OK : set_cuda_error(err, "group_mlp_max launch");
 }
@@ -631,6 +632,7 @@ extern "C" int elo_cost_volume_1(const elo_cost_volume_desc* d, void* stream)
         if ((rc = set_smem(cost_volume_1_kernel<2>, bytes, "cost_volume_1 smem"))) return rc;
         cost_volume_1_kernel<2><<<tc.tiles, CTA_THREADS, bytes, st>>>(p);
     }
+    count_launches(1);
     cudaError_t err = cudaGetLastError();
     return err == cudaSuccess ? ELO_OK : set_cuda_error(err, "cost_volume_1 launch");
 }
@@ -668,6 +670,7 @@ extern "C" int elo_cost_volume_2(const elo_cost_volume_desc* d, void* stream)
         if ((rc = set_smem(cost_volume_2_kernel<2>, bytes, "cost_volume_2 smem"))) return rc;
         cost_volume_2_kernel<2><<<tc.tiles, CTA_THREADS, bytes, st>>>(p);
     }
+    count_launches(1);
     cudaError_t err = cudaGetLastError();
     return err == cudaSuccess ? ELO_OK : set_cuda_error(err, "cost_volume_2 launch");
 }
@@ -736,6 +739,7 @@ extern "C" int elo_row_mlp(const elo_row_mlp_desc* d, void* stream)
         if ((rc = set_smem(row_mlp_kernel<2>, bytes, "row_mlp smem"))) return rc;
         row_mlp_kernel<2><<<grid, CTA_THREADS, bytes, st>>>(p);
     }
+    count_launches(1);
     cudaError_t err = cudaGetLastError();
     return err == cudaSuccess ? ELO_OK : set_cuda_error(err, "row_mlp launch");
 }

@@ -181,6 +181,7 @@ static int launch_index(bool select, int B, int H, int W, int N, int kH, int kW,
     } else {
         fused_conv_index_kernel<false><<<(unsigned)ctas, warps * 32, smem, stream>>>(p);
     }
+    count_launches(1);
     err = cudaGetLastError();
     if (err != cudaSuccess) return set_cuda_error(err, select ? "fused_conv_select_k launch" : "fused_conv_random_k launch");
     return ELO_OK;

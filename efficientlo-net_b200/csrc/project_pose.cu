@@ -325,6 +325,7 @@ extern "C" int elo_gt_pose(int batch_size, const float* T_gt, const float* T_tra
     if (batch_size == 0) return ELO_OK;
     gt_pose_kernel<<<(batch_size + 63) / 64, 64, 0, (cudaStream_t)stream>>>(batch_size, T_gt, T_trans, T_trans_inv,
                                                                            aug_frame, q_gt, t_gt);
+    count_launches(1);
     cudaError_t err = cudaGetLastError();
     return err == cudaSuccess ? ELO_OK : set_cuda_error(err, "gt_pose launch");
 }
@@ -357,6 +358,7 @@ extern "C" int elo_project(const elo_project_desc* d, void* stream)
     project_bin_kernel<<<blocks((long long)p.B * p.N), 256, 0, st>>>(p);
     const int slabs = 1 + (p.out_feat ? (p.C + 3) / 4 : 0);
     project_scatter_kernel<<<blocks((long long)p.B * p.N * slabs), 256, 0, st>>>(p);
+    count_launches(3);
     cudaError_t err = cudaGetLastError();
     return err == cudaSuccess ? ELO_OK : set_cuda_error(err, "project launch");
 }
@@ -379,6 +381,7 @@ extern "C" int elo_pose_head(const elo_pose_head_desc* d, void* stream)
     p.q_out = d->q_out; p.t_out = d->t_out; p.q_norm_out = d->q_norm_out; p.pooled_out = d->pooled_out;
     dim3 grid(p.G, p.B);
     pose_head_kernel<<<grid, POSE_THREADS, 0, (cudaStream_t)stream>>>(p);
+    count_launches(1);
     cudaError_t err = cudaGetLastError();
     return err == cudaSuccess ? ELO_OK : set_cuda_error(err, "pose_head launch");
 }

@@ -185,6 +185,7 @@ static int launch_small(const SmallParams& p, int nsets, cudaStream_t st)
         if (e != cudaSuccess) return set_cuda_error(e, "set_conv_small smem");
     }
     kern<<<dim3((unsigned)ctas, nsets), 256, smem, st>>>(p);
+    count_launches(1);
     cudaError_t err = cudaGetLastError();
     return err == cudaSuccess ? ELO_OK : set_cuda_error(err, "set_conv_small launch");
 }

@@ -74,8 +74,7 @@ def get_model(point_cloud, H_input, W_input, T_gt, T_trans, T_trans_inv, is_trai
     oh, ow = pyramid_shapes(H_input, W_input)
     K = keep if keep is not None else {}
     want = keep is not None
-    if aug_frame is None:
-        aug_frame = [2] * B
+    aug_list = [2] * B if aug_frame is None else aug_frame
 
     with use_store(store):
         # ---- PreProcess (:61) + ProjectPC2SphericalRing x2 (:63-64), both frames in one pass.
@@ -86,8 +85,8 @@ def get_model(point_cloud, H_input, W_input, T_gt, T_trans, T_trans_inv, is_trai
                                 eye if T_trans_inv is None else T_trans_inv.to(dev), aug_frame)
         T_aug = None
         if not _all_identity(T_trans):
-            T_aug = torch.cat([mu.aug_matrices(T_trans, aug_frame, 1, B, dev),
-                               mu.aug_matrices(T_trans, aug_frame, 2, B, dev)], 0)
+            T_aug = torch.cat([mu.aug_matrices(T_trans, aug_list, 1, B, dev),
+                               mu.aug_matrices(T_trans, aug_list, 2, B, dev)], 0)
         stride_pt, stride_b = point_cloud.stride(1), point_cloud.stride(0)
         xyz_in, _, _ = mu.project_points(point_cloud[:, :N, 0:3], None, H_input, W_input, mode=1, T=T_aug,
                                          inner_batch=B, outer_stride=N * stride_pt, batch_size=2 * B)

@@ -29,6 +29,7 @@ extern "C" {
 
 const char *elo_last_error(void);
 int elo_version(void);
+long long elo_launch_count(void); /* kernels launched by this library in this process so far */
 
 /*
  * Projection-aware neighbour search.  Same parameter list and meaning as the reference Launchers,
