@@ -149,7 +149,7 @@ def run_ours(args, rank, world, local_rank):
     host = [elo.synth.synth_batch(B, H_IN, W_IN, NPTS, seed0=rank * 1000 + i * B) for i in range(min(pool, 4))]
     engines = []
     for i in range(pool):
-        eng = elo.PWCLOEngine(B, H_IN, W_IN, NPTS, params=store, perms=perms, device=dev)
+        eng = elo.PWCLOEngine(B, H_IN, W_IN, NPTS, params=store, perms=perms, device=dev, use_graph=not args.no_graph)
         pc, T = host[i % len(host)]
         # make the pool's buffers distinct in content too (a rigid shift of the unique batches)
         eng.load(pc, T, non_blocking=False)
@@ -267,7 +267,8 @@ def run_ours(args, rank, world, local_rank):
                            "batch_per_gpu": B, "parallelism": "frame-pairs sharded over %d GPU(s), no collective" % world,
                            "l2": "inputs rotate over %d distinct batches (%.0f MB > 126 MB L2); weights stay resident"
                                  % (pool, pool * batch_bytes / 1e6),
-                           "graph": "whole forward captured as one CUDA graph"},
+                           "graph": "kernel-by-kernel launches (--no-graph)" if args.no_graph else
+                                    "whole forward captured as one CUDA graph"},
                 "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": "frame-pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": e2e_ms / args.steps},
@@ -316,6 +317,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-pairs", type=int, default=6)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="launch kernel by kernel (for ncu launch lists)")
     ap.add_argument("--pool", type=int, default=0, help="input batches to rotate (0 = enough to exceed L2)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)

@@ -28,7 +28,12 @@ class GroupMlpDesc(ctypes.Structure):
     _fields_ = [("batch_size", _c_int), ("queries", Queries), ("nsets", _c_int), ("set_batch_offset", _c_int * 2),
                 ("window", Window * 2), ("feat_channels", _c_int), ("num_layers", _c_int), ("cout", _c_int * 3),
                 ("xyz1", _c_void_p), ("xyz2", _c_void_p), ("feat2", _c_void_p * 2), ("weights", _c_void_p * 2),
-                ("out", _c_void_p * 2), ("dbg_nbr", _c_void_p * 2)]
+                ("out", _c_void_p * 2), ("dbg_nbr", _c_void_p * 2), ("nbr", _c_void_p * 2)]
+
+
+class SearchDesc(ctypes.Structure):
+    _fields_ = [("select", _c_int), ("batch_size", _c_int), ("queries", Queries), ("window", Window),
+                ("xyz1", _c_void_p), ("xyz2", _c_void_p), ("out_nbr", _c_void_p)]
 
 
 class CostVolumeDesc(ctypes.Structure):
@@ -36,7 +41,7 @@ class CostVolumeDesc(ctypes.Structure):
                 ("window_q", Window), ("window_p", Window),
                 ("xyz1", _c_void_p), ("xyz2", _c_void_p), ("f1", _c_void_p), ("f2", _c_void_p),
                 ("weights_1", _c_void_p), ("weights_2", _c_void_p), ("stage1_out", _c_void_p), ("out", _c_void_p),
-                ("dbg_nbr_q", _c_void_p), ("dbg_nbr_p", _c_void_p)]
+                ("dbg_nbr_q", _c_void_p), ("dbg_nbr_p", _c_void_p), ("nbr_q", _c_void_p), ("nbr_p", _c_void_p)]
 
 
 class RowMlpPhase(ctypes.Structure):
@@ -72,6 +77,7 @@ _FUSED_CONV = [_c_int] * 8 + [_c_float, _c_int, _c_int] + [_c_void_p] * 8 + [_c_
 SIGNATURES = {
     "elo_fused_conv_select_k": _FUSED_CONV,
     "elo_fused_conv_random_k": _FUSED_CONV,
+    "elo_multi_search": [ctypes.POINTER(SearchDesc), _c_int, _c_void_p],
     "elo_group_mlp_max": [ctypes.POINTER(GroupMlpDesc), _c_void_p],
     "elo_set_conv_small": [ctypes.POINTER(GroupMlpDesc), _c_void_p],
     "elo_cost_volume_1": [ctypes.POINTER(CostVolumeDesc), _c_void_p],
@@ -79,6 +85,8 @@ SIGNATURES = {
     "elo_row_mlp": [ctypes.POINTER(RowMlpDesc), _c_void_p],
     "elo_project": [ctypes.POINTER(ProjectDesc), _c_void_p],
     "elo_pose_head": [ctypes.POINTER(PoseHeadDesc), _c_void_p],
+    "elo_pyramid_xyz": [_c_int, _c_int, _c_int, ctypes.POINTER(_c_int), ctypes.POINTER(_c_int),
+                        ctypes.POINTER(_c_int), ctypes.POINTER(_c_int), _c_void_p, ctypes.POINTER(_c_void_p), _c_void_p],
     "elo_gt_pose": [_c_int, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p],
 }
 

@@ -36,10 +36,10 @@ struct Window {
 
 // Per-CTA table of window offsets in scan order: off[j] = (p / kW - kH/2, p % kW - kW/2), p = random_hw[j].
 __device__ __forceinline__ void build_offsets(int2* off, const int* __restrict__ random_hw,
-                                              int kt, int kH, int kW)
+                                              int kt, int kH, int kW, int nthreads)
 {
     const int hh = kH / 2, hw = kW / 2;
-    for (int j = threadIdx.x; j < kt; j += blockDim.x) {
+    for (int j = threadIdx.x; j < kt; j += nthreads) {
         const int p = __ldg(random_hw + j);
         off[j] = make_int2(p / kW - hh, p % kW - hw);
     }

@@ -45,7 +45,7 @@ __device__ __forceinline__ void tile_search(const QuerySet& qs, const Window& g,
                                             int qt, long long total_q, int* nbr, float* ctr, float* scratch_dist,
                                             int* scratch_hw)
 {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = COMPUTE_WARPS;
     const int nq = qs.oh * qs.ow;
     for (int ql = warp; ql < qt; ql += nwarps) {
         int* row = nbr + ql * g.K;
@@ -79,6 +79,32 @@ __device__ __forceinline__ void tile_search(const QuerySet& qs, const Window& g,
     }
 }
 
+// Same tables as tile_search, but read from a pre-computed nbr table (elo_multi_search) instead of searching.
+__device__ __forceinline__ void tile_load_nbr(const QuerySet& qs, int K, const float* __restrict__ xyz1,
+                                              const int* __restrict__ nbr_in, long long q0, int qt,
+                                              long long total_q, int* nbr, float* ctr)
+{
+    const int nq = qs.oh * qs.ow;
+    for (int t = threadIdx.x; t < qt * K; t += CTA_THREADS) {
+        const long long gq = q0 + t / K;
+        nbr[t] = gq < total_q ? __ldg(nbr_in + q0 * K + t) : -1;
+    }
+    for (int ql = threadIdx.x; ql < qt; ql += CTA_THREADS) {
+        const long long gq = q0 + ql;
+        float xc = 0.f, yc = 0.f, zc = 0.f;
+        int b = -1;
+        if (gq < total_q) {
+            int h, w;
+            b = (int)(gq / nq);
+            query_cell(qs, (int)(gq % nq), h, w);
+            const float* c = xyz1 + ((size_t)b * qs.H1 * qs.W1 + (size_t)h * qs.W1 + w) * 3;
+            xc = __ldg(c); yc = __ldg(c + 1); zc = __ldg(c + 2);
+        }
+        ctr[ql * 4 + 0] = xc; ctr[ql * 4 + 1] = yc; ctr[ql * 4 + 2] = zc;
+        ctr[ql * 4 + 3] = __int_as_float(b);
+    }
+}
+
 // X[c0 + c][r] = src[(b, cell(r)), c] for c < C (C % 4 == 0), zero for masked / padding rows.
 // cell_of(r) returns the linear row of `src` (>= 0) or -1.
 template <typename CellOf>
@@ -86,7 +112,7 @@ __device__ __forceinline__ void gather_features(float* X, int RS, int c0, const 
                                                 int rows, CellOf cell_of)
 {
     const int c4n = C >> 2;
-    for (int t = threadIdx.x; t < rows * c4n; t += blockDim.x) {
+    for (int t = threadIdx.x; t < rows * c4n; t += CTA_THREADS) {
         const int r = t / c4n, c4 = t - r * c4n;
         const long long cell = cell_of(r);
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);

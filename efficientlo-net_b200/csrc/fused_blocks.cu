@@ -29,7 +29,7 @@ struct GroupMlpParams {
     QuerySet qs;
     Window g;
     long long q_base[2], q_end[2];   // global query range of each parameter set
-    int qt, Cf, nl, cout[3], total_chunks;
+    int qt, Cf, nl, cout[3], total_chunks, nring;
     const float* xyz1;
     const float* xyz2;
     const float* feat2[2];
@@ -37,16 +37,17 @@ struct GroupMlpParams {
     const float* weights[2];
     float* out[2];
     int* dbg_nbr[2];
+    const int* nbr_in[2];
 };
 
 template <int NB>
-__global__ void __launch_bounds__(CTA_THREADS, 1) group_mlp_max_kernel(const GroupMlpParams p)
+__global__ void __launch_bounds__(LAUNCH_THREADS, 1) group_mlp_max_kernel(const GroupMlpParams p)
 {
     constexpr int RS = NB * 64;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     SmemCarver sc(smem_raw);
-    float* ring = sc.take<float>(RING * CHUNK_FLOATS);
-    uint64_t* bars = sc.take<uint64_t>(RING);
+    float* ring = sc.take<float>((size_t)p.nring * CHUNK_FLOATS);
+    uint64_t* bars = sc.take<uint64_t>(2 * MAX_RING);
     int2* off = sc.take<int2>(p.g.kt);
     int* nbr = sc.take<int>(RS);
     float* ctr = sc.take<float>(RS * 4);
@@ -58,19 +59,24 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) group_mlp_max_kernel(const Gro
     const int set = blockIdx.y;
     const Window g = p.g;
     WeightStream ws;
-    ws.start(p.weights[set], ring, bars, p.total_chunks, 1);
-    build_offsets(off, p.random_hw[set], g.kt, g.kH, g.kW);
-    for (int i = threadIdx.x; i < RS; i += blockDim.x) nbr[i] = -1;
-    __syncthreads();
+    ws.init(ring, bars, p.nring);
+    if (threadIdx.x >= CTA_THREADS) {            // producer warp: nothing but the weight stream
+        ws.produce(p.weights[set], p.total_chunks, 1);
+        return;
+    }
+    build_offsets(off, p.random_hw[set], g.kt, g.kH, g.kW, CTA_THREADS);
+    for (int i = threadIdx.x; i < RS; i += CTA_THREADS) nbr[i] = -1;
+    compute_sync();
 
     const long long q0 = p.q_base[set] + (long long)blockIdx.x * p.qt;
     const long long total_q = p.q_end[set];
     const int cells2 = g.h2 * g.w2;
-    tile_search<false>(p.qs, g, p.xyz1, p.xyz2, off, q0, p.qt, total_q, nbr, ctr, nullptr, nullptr);
-    __syncthreads();
+    if (p.nbr_in[set] != nullptr) tile_load_nbr(p.qs, g.K, p.xyz1, p.nbr_in[set], q0, p.qt, total_q, nbr, ctr);
+    else tile_search<false>(p.qs, g, p.xyz1, p.xyz2, off, q0, p.qt, total_q, nbr, ctr, nullptr, nullptr);
+    compute_sync();
 
     // first layer input: [q_k - p (3), feat2_k (Cf)], masked neighbours contribute q = 0, feat = 0
-    for (int r = threadIdx.x; r < RS; r += blockDim.x) {
+    for (int r = threadIdx.x; r < RS; r += CTA_THREADS) {
         const int q = r / g.K;
         float dx = 0.f, dy = 0.f, dz = 0.f;
         if (q < p.qt) {
@@ -98,7 +104,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) group_mlp_max_kernel(const Gro
             return (long long)__float_as_int(ctr[q * 4 + 3]) * cells2 + nbr[r];
         });
     }
-    __syncthreads();
+    compute_sync();
 
     const float* in = X;
     int cin = cin0;
@@ -112,7 +118,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) group_mlp_max_kernel(const Gro
     // max over the K neighbours of (y * mask): y >= 0 after ReLU, masked rows count as 0
     const int Cout = cin;
     float* out = p.out[set];
-    for (int t = threadIdx.x; t < p.qt * Cout; t += blockDim.x) {
+    for (int t = threadIdx.x; t < p.qt * Cout; t += CTA_THREADS) {
         const int q = t / Cout, c = t - q * Cout;
         const long long gq = q0 + q;
         if (gq >= total_q) break;
@@ -122,7 +128,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) group_mlp_max_kernel(const Gro
         out[gq * Cout + c] = m;
     }
     if (p.dbg_nbr[set] != nullptr)
-        for (int t = threadIdx.x; t < p.qt * g.K; t += blockDim.x)
+        for (int t = threadIdx.x; t < p.qt * g.K; t += CTA_THREADS)
             if (q0 + t / g.K < total_q) p.dbg_nbr[set][q0 * g.K + t] = nbr[t];
 }
 
@@ -132,7 +138,7 @@ struct Cv1Params {
     QuerySet qs;
     Window g;
     long long total_q;
-    int qt, C, total_chunks;
+    int qt, C, total_chunks, nring;
     const float* xyz1;
     const float* xyz2;
     const float* f1;
@@ -141,6 +147,7 @@ struct Cv1Params {
     const float* weights;
     float* out;
     int* dbg_nbr;
+    const int* nbr_in;
 };
 
 // xyz part of a cost-volume row: [p, q, q - p, sqrt(|q - p|^2 + 1e-20)] (utils/pointnet_util.py:60-63)
@@ -175,13 +182,13 @@ __device__ __forceinline__ float softmax_pool(const float* logit, const float* v
 }
 
 template <int NB>
-__global__ void __launch_bounds__(CTA_THREADS, 1) cost_volume_1_kernel(const Cv1Params p)
+__global__ void __launch_bounds__(LAUNCH_THREADS, 1) cost_volume_1_kernel(const Cv1Params p)
 {
     constexpr int RS = NB * 64;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     SmemCarver sc(smem_raw);
-    float* ring = sc.take<float>(RING * CHUNK_FLOATS);
-    uint64_t* bars = sc.take<uint64_t>(RING);
+    float* ring = sc.take<float>((size_t)p.nring * CHUNK_FLOATS);
+    uint64_t* bars = sc.take<uint64_t>(2 * MAX_RING);
     int2* off = sc.take<int2>(p.g.kt);
     int* nbr = sc.take<int>(RS);
     float* ctr = sc.take<float>(RS * 4);
@@ -193,19 +200,24 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) cost_volume_1_kernel(const Cv1
 
     const Window g = p.g;
     WeightStream ws;
-    ws.start(p.weights, ring, bars, p.total_chunks, 1);
-    build_offsets(off, p.random_hw, g.kt, g.kH, g.kW);
-    for (int i = threadIdx.x; i < RS; i += blockDim.x) nbr[i] = -1;
-    __syncthreads();
+    ws.init(ring, bars, p.nring);
+    if (threadIdx.x >= CTA_THREADS) {            // producer warp: nothing but the weight stream
+        ws.produce(p.weights, p.total_chunks, 1);
+        return;
+    }
+    build_offsets(off, p.random_hw, g.kt, g.kH, g.kW, CTA_THREADS);
+    for (int i = threadIdx.x; i < RS; i += CTA_THREADS) nbr[i] = -1;
+    compute_sync();
 
     const long long q0 = (long long)blockIdx.x * p.qt;
-    const int cells = g.h2 * g.w2, nwarps = blockDim.x >> 5;
+    const int cells = g.h2 * g.w2, nwarps = COMPUTE_WARPS;
     float* sdist = A;
     int* shw = reinterpret_cast<int*>(A + (size_t)nwarps * g.kt);
-    tile_search<true>(p.qs, g, p.xyz1, p.xyz2, off, q0, p.qt, p.total_q, nbr, ctr, sdist, shw);
-    __syncthreads();
+    if (p.nbr_in != nullptr) tile_load_nbr(p.qs, g.K, p.xyz1, p.nbr_in, q0, p.qt, p.total_q, nbr, ctr);
+    else tile_search<true>(p.qs, g, p.xyz1, p.xyz2, off, q0, p.qt, p.total_q, nbr, ctr, sdist, shw);
+    compute_sync();
 
-    for (int r = threadIdx.x; r < RS; r += blockDim.x) {
+    for (int r = threadIdx.x; r < RS; r += CTA_THREADS) {
         const int q = r / g.K;
         float px = 0.f, py = 0.f, pz = 0.f, qx = 0.f, qy = 0.f, qz = 0.f;
         if (q < p.qt) {
@@ -235,7 +247,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) cost_volume_1_kernel(const Cv1
             return (long long)((q0 + q) / nq) * cells + nbr[r];
         });
     }
-    __syncthreads();
+    compute_sync();
 
     dense<NB, 128, true>(ws, X, xc, A);            // CV_0
     dense<NB, 64, true>(ws, A, 128, Cb);           // CV_1
@@ -244,14 +256,14 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) cost_volume_1_kernel(const Cv1
     dense<NB, 128, true>(ws, Bf, 128, A);          // sum_CV_0 on [enc, F]
     dense<NB, 64, true>(ws, A, 128, Cb);           // sum_CV_1  -> attention logits
 
-    for (int t = threadIdx.x; t < p.qt * 64; t += blockDim.x) {
+    for (int t = threadIdx.x; t < p.qt * 64; t += CTA_THREADS) {
         const int q = t >> 6, c = t & 63;
         const long long gq = q0 + q;
         if (gq >= p.total_q) break;
         p.out[gq * 64 + c] = softmax_pool(Cb, Bf + 64 * RS, nbr + q * g.K, c, q * g.K, g.K, RS);
     }
     if (p.dbg_nbr != nullptr)
-        for (int t = threadIdx.x; t < p.qt * g.K; t += blockDim.x)
+        for (int t = threadIdx.x; t < p.qt * g.K; t += CTA_THREADS)
             if (q0 + t / g.K < p.total_q) p.dbg_nbr[q0 * g.K + t] = nbr[t];
 }
 
@@ -261,7 +273,7 @@ struct Cv2Params {
     QuerySet qs;
     Window g;
     long long total_q;
-    int qt, C, total_chunks;
+    int qt, C, total_chunks, nring;
     const float* xyz1;
     const float* f1;
     const float* cv1;
@@ -269,16 +281,17 @@ struct Cv2Params {
     const float* weights;
     float* out;
     int* dbg_nbr;
+    const int* nbr_in;
 };
 
 template <int NB>
-__global__ void __launch_bounds__(CTA_THREADS, 1) cost_volume_2_kernel(const Cv2Params p)
+__global__ void __launch_bounds__(LAUNCH_THREADS, 1) cost_volume_2_kernel(const Cv2Params p)
 {
     constexpr int RS = NB * 64;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     SmemCarver sc(smem_raw);
-    float* ring = sc.take<float>(RING * CHUNK_FLOATS);
-    uint64_t* bars = sc.take<uint64_t>(RING);
+    float* ring = sc.take<float>((size_t)p.nring * CHUNK_FLOATS);
+    uint64_t* bars = sc.take<uint64_t>(2 * MAX_RING);
     int2* off = sc.take<int2>(p.g.kt);
     int* nbr = sc.take<int>(RS);
     float* ctr = sc.take<float>(RS * 4);
@@ -290,17 +303,22 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) cost_volume_2_kernel(const Cv2
 
     const Window g = p.g;
     WeightStream ws;
-    ws.start(p.weights, ring, bars, p.total_chunks, 1);
-    build_offsets(off, p.random_hw, g.kt, g.kH, g.kW);
-    for (int i = threadIdx.x; i < RS; i += blockDim.x) nbr[i] = -1;
-    __syncthreads();
+    ws.init(ring, bars, p.nring);
+    if (threadIdx.x >= CTA_THREADS) {            // producer warp: nothing but the weight stream
+        ws.produce(p.weights, p.total_chunks, 1);
+        return;
+    }
+    build_offsets(off, p.random_hw, g.kt, g.kH, g.kW, CTA_THREADS);
+    for (int i = threadIdx.x; i < RS; i += CTA_THREADS) nbr[i] = -1;
+    compute_sync();
 
     const long long q0 = (long long)blockIdx.x * p.qt;
     const int cells = g.h2 * g.w2;
-    tile_search<false>(p.qs, g, p.xyz1, p.xyz1, off, q0, p.qt, p.total_q, nbr, ctr, nullptr, nullptr);
-    __syncthreads();
+    if (p.nbr_in != nullptr) tile_load_nbr(p.qs, g.K, p.xyz1, p.nbr_in, q0, p.qt, p.total_q, nbr, ctr);
+    else tile_search<false>(p.qs, g, p.xyz1, p.xyz1, off, q0, p.qt, p.total_q, nbr, ctr, nullptr, nullptr);
+    compute_sync();
 
-    for (int r = threadIdx.x; r < RS; r += blockDim.x) {
+    for (int r = threadIdx.x; r < RS; r += CTA_THREADS) {
         const int q = r / g.K;
         float px = 0.f, py = 0.f, pz = 0.f, qx = 0.f, qy = 0.f, qz = 0.f;
         if (q < p.qt) {
@@ -329,7 +347,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) cost_volume_2_kernel(const Cv2
             return (long long)((q0 + q) / nq) * cells + nbr[r];
         });
     }
-    __syncthreads();
+    compute_sync();
 
     dense<NB, 64, true>(ws, Y, 10, X);              // sum_xyz_encoding -> X[0:64]
     dense<NB, 128, true>(ws, X, 128 + C, A);        // sum_cost_volume_0 on [enc, f1, stage-1 of neighbour]
@@ -337,7 +355,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) cost_volume_2_kernel(const Cv2
 
     // weights applied to the gathered stage-1 features, which sit at channel 64 + C (any alignment:
     // softmax_pool indexes through act_index with absolute channels)
-    for (int t = threadIdx.x; t < p.qt * 64; t += blockDim.x) {
+    for (int t = threadIdx.x; t < p.qt * 64; t += CTA_THREADS) {
         const int q = t >> 6, c = t & 63;
         const long long gq = q0 + q;
         if (gq >= p.total_q) break;
@@ -355,7 +373,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) cost_volume_2_kernel(const Cv2
         p.out[gq * 64 + c] = acc / s;
     }
     if (p.dbg_nbr != nullptr)
-        for (int t = threadIdx.x; t < p.qt * g.K; t += blockDim.x)
+        for (int t = threadIdx.x; t < p.qt * g.K; t += CTA_THREADS)
             if (q0 + t / g.K < p.total_q) p.dbg_nbr[q0 * g.K + t] = nbr[t];
 }
 
@@ -370,7 +388,7 @@ struct RowMlpParams {
     int src_c[2][3];           // channels of each source
     int src_prev[2][3];        // 1: the source is the previous phase's output (kept in shared memory)
     int nl[2], cout[2][3];
-    int total_chunks;
+    int total_chunks, nring;
     const float* src[2][2][3]; // [set][phase][i]
     const float* weights[2];
     float* out[2];
@@ -378,13 +396,13 @@ struct RowMlpParams {
 };
 
 template <int NB>
-__global__ void __launch_bounds__(CTA_THREADS, 1) row_mlp_kernel(const RowMlpParams p)
+__global__ void __launch_bounds__(LAUNCH_THREADS, 1) row_mlp_kernel(const RowMlpParams p)
 {
     constexpr int RS = NB * 64;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     SmemCarver sc(smem_raw);
-    float* ring = sc.take<float>(RING * CHUNK_FLOATS);
-    uint64_t* bars = sc.take<uint64_t>(RING);
+    float* ring = sc.take<float>((size_t)p.nring * CHUNK_FLOATS);
+    uint64_t* bars = sc.take<uint64_t>(2 * MAX_RING);
     int xmax = 0;
     for (int ph = 0; ph < p.nphase; ++ph) {
         int c = 0;
@@ -397,7 +415,11 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) row_mlp_kernel(const RowMlpPar
 
     const int set = blockIdx.y;
     WeightStream ws;
-    ws.start(p.weights[set], ring, bars, p.total_chunks, 1);
+    ws.init(ring, bars, p.nring);
+    if (threadIdx.x >= CTA_THREADS) {
+        ws.produce(p.weights[set], p.total_chunks, 1);
+        return;
+    }
     const long long r0 = (long long)blockIdx.x * p.rt;
     const long long rows = p.rows;
     const int rt = p.rt;
@@ -409,7 +431,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) row_mlp_kernel(const RowMlpPar
         for (int i = 0; i < p.nsrc[ph]; ++i) {
             const int Ci = p.src_c[ph][i];
             if (p.src_prev[ph][i]) {
-                for (int t = threadIdx.x; t < RS * prev_c; t += blockDim.x) {
+                for (int t = threadIdx.x; t < RS * prev_c; t += CTA_THREADS) {
                     const int c = t / RS, r = t - c * RS;
                     X[act_index(c0 + c, r, RS)] = prev[act_index(c, r, RS)];
                 }
@@ -420,7 +442,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) row_mlp_kernel(const RowMlpPar
             }
             c0 += Ci;
         }
-        __syncthreads();
+        compute_sync();
         const float* in = X;
         int cin = c0;
         for (int l = 0; l < p.nl[ph]; ++l) {
@@ -433,7 +455,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) row_mlp_kernel(const RowMlpPar
         prev_c = cin;
         float* dst = (ph == p.nphase - 1) ? p.out[set] : p.out_phase0[set];
         if (dst != nullptr)
-            for (int t = threadIdx.x; t < rt * cin; t += blockDim.x) {
+            for (int t = threadIdx.x; t < rt * cin; t += CTA_THREADS) {
                 const int r = t / cin, c = t - r * cin;
                 if (r0 + r >= rows) break;
                 dst[(r0 + r) * cin + c] = in[act_index(c, r, RS)];
@@ -457,7 +479,7 @@ static TileChoice choose_tile(long long units, int rows_per_unit, int nsets, Sme
     TileChoice best{0, 0, 0};
     double best_cost = 1e30;
     for (int nb = 1; nb <= 2; ++nb) {
-        if (smem_bytes(nb) > (size_t)SMEM_LIMIT) continue;
+        if (smem_bytes(nb) + 2 * CHUNK_BYTES > (size_t)SMEM_LIMIT) continue;
         const int cap = (64 * nb) / rows_per_unit;
         if (cap < 1) continue;
         long long tiles = (units + cap - 1) / cap;
@@ -488,10 +510,19 @@ static int set_smem(Kernel k, size_t bytes, const char* what)
 
 static size_t align16(size_t b) { return (b + 15) & ~size_t(15); }
 
+// shared memory besides the weight ring: barriers, offset table, row->cell table, centres
 static size_t common_smem(int kt, int rs)
 {
-    return align16(RING_BYTES) + align16(RING * 8) + align16((size_t)kt * 8) + align16((size_t)rs * 4) +
-           align16((size_t)rs * 16);
+    return align16(2 * MAX_RING * 8) + align16((size_t)kt * 8) + align16((size_t)rs * 4) + align16((size_t)rs * 16);
+}
+
+// ring depth: as many 8 KB chunks as fit next to `base` bytes, 2..MAX_RING, no more than the stream has
+static int pick_ring(size_t base, int total_chunks)
+{
+    long long n = ((long long)SMEM_LIMIT - (long long)base) / CHUNK_BYTES;
+    if (n > MAX_RING) n = MAX_RING;
+    if (n > total_chunks) n = total_chunks;
+    return (int)n;
 }
 
 static int check_window(const elo_window* w, const char* who)
@@ -568,7 +599,7 @@ extern "C" int elo_group_mlp_max(const elo_group_mlp_desc* d, void* stream)
         if (!d->feat2[u] || !d->weights[u] || !d->out[u] || !d->window[u].random_hw)
             return set_error(ELO_ERR_INVALID_ARGUMENT, "group_mlp_max: null pointer");
         p.feat2[s] = d->feat2[u]; p.random_hw[s] = d->window[u].random_hw; p.weights[s] = d->weights[u];
-        p.out[s] = d->out[u]; p.dbg_nbr[s] = d->dbg_nbr[u];
+        p.out[s] = d->out[u]; p.dbg_nbr[s] = d->dbg_nbr[u]; p.nbr_in[s] = d->nbr[u];
         if (d->set_batch_offset[u] < 0) return set_error(ELO_ERR_INVALID_ARGUMENT, "group_mlp_max: negative batch offset");
         p.q_base[s] = (long long)d->set_batch_offset[u] * p.qs.oh * p.qs.ow;
         p.q_end[s] = p.q_base[s] + per_set;
@@ -579,14 +610,15 @@ extern "C" int elo_group_mlp_max(const elo_group_mlp_desc* d, void* stream)
     if (tc.nb == 0) return set_error(ELO_ERR_UNSUPPORTED, "group_mlp_max: tile does not fit shared memory");
     p.qt = tc.per_tile;
     dim3 grid(tc.tiles, d->nsets);
-    const size_t bytes = smem(tc.nb);
+    p.nring = pick_ring(smem(tc.nb), p.total_chunks);
+    const size_t bytes = smem(tc.nb) + (size_t)p.nring * CHUNK_BYTES;
     cudaStream_t st = (cudaStream_t)stream;
     if (tc.nb == 1) {
         if ((rc = set_smem(group_mlp_max_kernel<1>, bytes, "group_mlp_max smem"))) return rc;
-        group_mlp_max_kernel<1><<<grid, CTA_THREADS, bytes, st>>>(p);
+        group_mlp_max_kernel<1><<<grid, LAUNCH_THREADS, bytes, st>>>(p);
     } else {
         if ((rc = set_smem(group_mlp_max_kernel<2>, bytes, "group_mlp_max smem"))) return rc;
-        group_mlp_max_kernel<2><<<grid, CTA_THREADS, bytes, st>>>(p);
+        group_mlp_max_kernel<2><<<grid, LAUNCH_THREADS, bytes, st>>>(p);
     }
     count_launches(1);
     cudaError_t err = cudaGetLastError();
@@ -613,7 +645,7 @@ extern "C" int elo_cost_volume_1(const elo_cost_volume_desc* d, void* stream)
     p.total_chunks = layer_chunks(xc, 128) + layer_chunks(128, 64) + layer_chunks(64, 64) + layer_chunks(10, 64) +
                      layer_chunks(128, 128) + layer_chunks(128, 64);
     p.xyz1 = d->xyz1; p.xyz2 = d->xyz2; p.f1 = d->f1; p.f2 = d->f2; p.random_hw = d->window_q.random_hw;
-    p.weights = d->weights_1; p.out = d->stage1_out; p.dbg_nbr = d->dbg_nbr_q;
+    p.weights = d->weights_1; p.out = d->stage1_out; p.dbg_nbr = d->dbg_nbr_q; p.nbr_in = d->nbr_q;
     const int kt = p.g.kt, xch = (xc + 3) & ~3;
     auto smem = [&](int nb) {
         // the select-K scratch (8 warps x kt x 8 B) must fit in the A|Bf|Cb region it aliases
@@ -623,14 +655,15 @@ extern "C" int elo_cost_volume_1(const elo_cost_volume_desc* d, void* stream)
     const TileChoice tc = choose_tile(p.total_q, p.g.K, 1, smem);
     if (tc.nb == 0) return set_error(ELO_ERR_UNSUPPORTED, "cost_volume_1: tile does not fit shared memory");
     p.qt = tc.per_tile;
-    const size_t bytes = smem(tc.nb);
+    p.nring = pick_ring(smem(tc.nb), p.total_chunks);
+    const size_t bytes = smem(tc.nb) + (size_t)p.nring * CHUNK_BYTES;
     cudaStream_t st = (cudaStream_t)stream;
     if (tc.nb == 1) {
         if ((rc = set_smem(cost_volume_1_kernel<1>, bytes, "cost_volume_1 smem"))) return rc;
-        cost_volume_1_kernel<1><<<tc.tiles, CTA_THREADS, bytes, st>>>(p);
+        cost_volume_1_kernel<1><<<tc.tiles, LAUNCH_THREADS, bytes, st>>>(p);
     } else {
         if ((rc = set_smem(cost_volume_1_kernel<2>, bytes, "cost_volume_1 smem"))) return rc;
-        cost_volume_1_kernel<2><<<tc.tiles, CTA_THREADS, bytes, st>>>(p);
+        cost_volume_1_kernel<2><<<tc.tiles, LAUNCH_THREADS, bytes, st>>>(p);
     }
     count_launches(1);
     cudaError_t err = cudaGetLastError();
@@ -655,20 +688,21 @@ extern "C" int elo_cost_volume_2(const elo_cost_volume_desc* d, void* stream)
     p.C = d->C;
     p.total_chunks = layer_chunks(10, 64) + layer_chunks(128 + d->C, 128) + layer_chunks(128, 64);
     p.xyz1 = d->xyz1; p.f1 = d->f1; p.cv1 = d->stage1_out; p.random_hw = d->window_p.random_hw;
-    p.weights = d->weights_2; p.out = d->out; p.dbg_nbr = d->dbg_nbr_p;
+    p.weights = d->weights_2; p.out = d->out; p.dbg_nbr = d->dbg_nbr_p; p.nbr_in = d->nbr_p;
     const int kt = p.g.kt;
     auto smem = [&](int nb) { return common_smem(kt, 64 * nb) + (size_t)(12 + 128 + d->C + 192) * 64 * nb * 4; };
     const TileChoice tc = choose_tile(p.total_q, p.g.K, 1, smem);
     if (tc.nb == 0) return set_error(ELO_ERR_UNSUPPORTED, "cost_volume_2: tile does not fit shared memory");
     p.qt = tc.per_tile;
-    const size_t bytes = smem(tc.nb);
+    p.nring = pick_ring(smem(tc.nb), p.total_chunks);
+    const size_t bytes = smem(tc.nb) + (size_t)p.nring * CHUNK_BYTES;
     cudaStream_t st = (cudaStream_t)stream;
     if (tc.nb == 1) {
         if ((rc = set_smem(cost_volume_2_kernel<1>, bytes, "cost_volume_2 smem"))) return rc;
-        cost_volume_2_kernel<1><<<tc.tiles, CTA_THREADS, bytes, st>>>(p);
+        cost_volume_2_kernel<1><<<tc.tiles, LAUNCH_THREADS, bytes, st>>>(p);
     } else {
         if ((rc = set_smem(cost_volume_2_kernel<2>, bytes, "cost_volume_2 smem"))) return rc;
-        cost_volume_2_kernel<2><<<tc.tiles, CTA_THREADS, bytes, st>>>(p);
+        cost_volume_2_kernel<2><<<tc.tiles, LAUNCH_THREADS, bytes, st>>>(p);
     }
     count_launches(1);
     cudaError_t err = cudaGetLastError();
@@ -724,20 +758,21 @@ extern "C" int elo_row_mlp(const elo_row_mlp_desc* d, void* stream)
             }
     }
     const int xch = (xmax + 3) & ~3;
-    auto smem = [&](int nb) { return align16(RING_BYTES) + align16(RING * 8) + (size_t)(xch + 256) * 64 * nb * 4; };
+    auto smem = [&](int nb) { return align16(2 * MAX_RING * 8) + (size_t)(xch + 256) * 64 * nb * 4; };
     const TileChoice tc = choose_tile(p.rows, 1, d->nsets, smem);
     if (tc.nb == 0) return set_error(ELO_ERR_UNSUPPORTED, "row_mlp: tile does not fit shared memory");
     p.rt = tc.per_tile;
     dim3 grid(tc.tiles, d->nsets);
-    const size_t bytes = smem(tc.nb);
+    p.nring = pick_ring(smem(tc.nb), p.total_chunks);
+    const size_t bytes = smem(tc.nb) + (size_t)p.nring * CHUNK_BYTES;
     cudaStream_t st = (cudaStream_t)stream;
     int rc;
     if (tc.nb == 1) {
         if ((rc = set_smem(row_mlp_kernel<1>, bytes, "row_mlp smem"))) return rc;
-        row_mlp_kernel<1><<<grid, CTA_THREADS, bytes, st>>>(p);
+        row_mlp_kernel<1><<<grid, LAUNCH_THREADS, bytes, st>>>(p);
     } else {
         if ((rc = set_smem(row_mlp_kernel<2>, bytes, "row_mlp smem"))) return rc;
-        row_mlp_kernel<2><<<grid, CTA_THREADS, bytes, st>>>(p);
+        row_mlp_kernel<2><<<grid, LAUNCH_THREADS, bytes, st>>>(p);
     }
     count_launches(1);
     cudaError_t err = cudaGetLastError();

@@ -19,6 +19,7 @@
 #include "../../include/elo_b200.h"
 #include "elo_common.cuh"
 #include "elo_search.cuh"
+#include "elo_tile.cuh"
 
 namespace elo {
 
@@ -71,7 +72,7 @@ __global__ void __launch_bounds__(256) fused_conv_index_kernel(const IndexParams
         dist = dist_all + (size_t)warp * g.kt;
         hw = hw_all + (size_t)warp * g.kt;
     }
-    build_offsets(off, p.random_hw, g.kt, g.kH, g.kW);
+    build_offsets(off, p.random_hw, g.kt, g.kH, g.kW, blockDim.x);
     __syncthreads();
 
     for (long long q = (long long)blockIdx.x * nwarps + warp; q < p.total;
@@ -119,6 +120,68 @@ __global__ void __launch_bounds__(256) fused_conv_index_kernel(const IndexParams
         fill_slots(o_idx, o_mask, filled, g.K, copy, b, c.first, lane);
         fill_counts(o_valid, g.kt, c.nvalid, lane);
         fill_counts(o_vdis, g.kt, c.nsel, lane);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Batched search: up to ELO_MAX_SEARCH independent neighbour searches in ONE launch, each writing the
+// compact table the fused blocks consume: nbr[b, n, k] = linear cell (hh * small_w + ww) of the k-th
+// selected neighbour in the searched grid, -1 where the reference's mask is 0.  Every search of the
+// network that depends on the same xyz grids runs together (all 11 of the un-warped pyramid; the 4 of
+// a refinement level), thousands of warps in flight instead of a few per GEMM tile.
+struct SearchSpec {
+    QuerySet qs;
+    Window g;
+    int select;
+    long long total_q;        // batch * oh * ow
+    int cta_begin;            // first CTA of this spec
+    const float* xyz1;
+    const float* xyz2;
+    const int* random_hw;
+    int* out_nbr;
+};
+
+struct MultiSearchParams {
+    int nspec;
+    SearchSpec spec[ELO_MAX_SEARCH];
+};
+
+__global__ void __launch_bounds__(256) multi_search_kernel(const __grid_constant__ MultiSearchParams p)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    int si = 0;
+    while (si + 1 < p.nspec && (int)blockIdx.x >= p.spec[si + 1].cta_begin) ++si;
+    const SearchSpec& sp = p.spec[si];
+    const Window g = sp.g;
+    const int nwarps = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int2* off = reinterpret_cast<int2*>(smem_raw);
+    float* dist = reinterpret_cast<float*>(off + g.kt) + (size_t)warp * g.kt;
+    int* hw = reinterpret_cast<int*>(reinterpret_cast<float*>(off + g.kt) + (size_t)nwarps * g.kt) + (size_t)warp * g.kt;
+    build_offsets(off, sp.random_hw, g.kt, g.kH, g.kW, blockDim.x);
+    __syncthreads();
+    const int nq = sp.qs.oh * sp.qs.ow;
+    const int cta_end = (si + 1 < p.nspec) ? p.spec[si + 1].cta_begin : (int)gridDim.x;
+    const int ctas = cta_end - sp.cta_begin;
+    for (long long q = (long long)((int)blockIdx.x - sp.cta_begin) * nwarps + warp; q < sp.total_q;
+         q += (long long)ctas * nwarps) {
+        int* row = sp.out_nbr + q * g.K;
+        for (int k = lane; k < g.K; k += 32) row[k] = -1;
+        const int b = (int)(q / nq);
+        int h, w;
+        query_cell(sp.qs, (int)(q % nq), h, w);
+        const float* c = sp.xyz1 + ((size_t)b * sp.qs.H1 * sp.qs.W1 + (size_t)h * sp.qs.W1 + w) * 3;
+        const float xc = __ldg(c), yc = __ldg(c + 1), zc = __ldg(c + 2);
+        __syncwarp();
+        if (fmaxf(sq3(xc, yc, zc), 1e-10f) <= 1e-10f) continue;
+        const float* g2 = sp.xyz2 + (size_t)b * g.h2 * g.w2 * 3;
+        auto emit = [&](int slot, int hh, int ww) { row[slot] = hh * g.w2 + ww; };
+        if (sp.select) {
+            int written;
+            search_select_k(g2, off, g, h / g.stride_h, w / g.stride_w, xc, yc, zc, dist, hw, &written, emit);
+        } else {
+            search_random_k(g2, off, g, h / g.stride_h, w / g.stride_w, xc, yc, zc, emit);
+        }
+        __syncwarp();
     }
 }
 
@@ -188,6 +251,61 @@ static int launch_index(bool select, int B, int H, int W, int N, int kH, int kW,
 }
 
 }  // namespace elo
+
+extern "C" int elo_multi_search(const elo_search_desc* specs, int nspec, void* stream)
+{
+    using namespace elo;
+    if (!specs || nspec < 1 || nspec > ELO_MAX_SEARCH)
+        return set_error(ELO_ERR_INVALID_ARGUMENT, "multi_search: 1..ELO_MAX_SEARCH specs");
+    MultiSearchParams p;
+    p.nspec = 0;
+    const int sms = device_info().sm_count;
+    const int warps = 8;
+    size_t smem = 0;
+    long long ctas_total = 0;
+    for (int i = 0; i < nspec; ++i) {
+        const elo_search_desc* d = &specs[i];
+        const elo_window* w = &d->window;
+        if (w->kernel_size_H <= 0 || w->kernel_size_W <= 0 || w->K <= 0 || !(w->distance > 0) || w->stride_h <= 0 ||
+            w->stride_w <= 0 || w->small_h <= 0 || w->small_w <= 0 || !w->random_hw || !d->xyz1 || !d->xyz2 ||
+            !d->out_nbr || d->batch_size < 0 || d->queries.H <= 0 || d->queries.W <= 0 || d->queries.out_h <= 0 ||
+            d->queries.out_w <= 0 || d->queries.q_stride_h <= 0 || d->queries.q_stride_w <= 0 ||
+            (d->queries.out_h - 1) * d->queries.q_stride_h >= d->queries.H ||
+            (d->queries.out_w - 1) * d->queries.q_stride_w >= d->queries.W)
+            return set_error(ELO_ERR_INVALID_ARGUMENT, "multi_search: bad spec");
+        const long long kt = (long long)w->kernel_size_H * w->kernel_size_W;
+        if (kt > 5000 || w->K > 5000 || w->small_h >= 32768 || w->small_w >= 32768)
+            return set_error(ELO_ERR_UNSUPPORTED, "multi_search: window / K limited to 5000, grids to 32767");
+        if (d->batch_size == 0) continue;
+        SearchSpec& sp = p.spec[p.nspec++];
+        sp.qs.H1 = d->queries.H; sp.qs.W1 = d->queries.W; sp.qs.oh = d->queries.out_h; sp.qs.ow = d->queries.out_w;
+        sp.qs.qs_h = d->queries.q_stride_h; sp.qs.qs_w = d->queries.q_stride_w;
+        sp.g.h2 = w->small_h; sp.g.w2 = w->small_w; sp.g.kH = w->kernel_size_H; sp.g.kW = w->kernel_size_W;
+        sp.g.kt = (int)kt; sp.g.stride_h = w->stride_h; sp.g.stride_w = w->stride_w; sp.g.K = w->K;
+        sp.g.flag_copy = 0; sp.g.d2max = w->distance * w->distance;
+        sp.select = d->select ? 1 : 0;
+        sp.total_q = (long long)d->batch_size * sp.qs.oh * sp.qs.ow;
+        sp.xyz1 = d->xyz1; sp.xyz2 = d->xyz2; sp.random_hw = w->random_hw; sp.out_nbr = d->out_nbr;
+        long long ctas = (sp.total_q + warps - 1) / warps;
+        const long long cap = (long long)sms * 8;
+        if (ctas > cap) ctas = cap;
+        sp.cta_begin = (int)ctas_total;
+        ctas_total += ctas;
+        const size_t need = (size_t)kt * 8 + (d->select ? (size_t)kt * 8 * warps : 0);
+        if (need > smem) smem = need;
+    }
+    if (p.nspec == 0) return ELO_OK;
+    if (smem > 200 * 1024) return set_error(ELO_ERR_UNSUPPORTED, "multi_search: window too large for one CTA");
+    cudaError_t err;
+    if (smem > 48 * 1024) {
+        err = cudaFuncSetAttribute(multi_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (err != cudaSuccess) return set_cuda_error(err, "cudaFuncSetAttribute(multi_search)");
+    }
+    multi_search_kernel<<<(unsigned)ctas_total, warps * 32, smem, (cudaStream_t)stream>>>(p);
+    count_launches(1);
+    err = cudaGetLastError();
+    return err == cudaSuccess ? ELO_OK : set_cuda_error(err, "multi_search launch");
+}
 
 extern "C" int elo_fused_conv_select_k(int batch_size, int H, int W, int npoints, int kernel_size_H,
                                        int kernel_size_W, int K, int flag_copy, float distance,

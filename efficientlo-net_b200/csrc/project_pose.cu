@@ -118,8 +118,13 @@ __global__ void project_bin_kernel(const ProjParams p)
         float x, y, z, r;
         transform_point(p, b, n, x, y, z);
         const int cell = bin_point(p, x, y, z, r);
-        // r >= 0 (or NaN, which orders above every finite value as an unsigned pattern)
-        atomicMin(p.cellmin + (size_t)b * p.H * p.W + cell, __float_as_uint(r));
+        // r >= 0 (or NaN, which orders above every finite value as an unsigned pattern).  Zero-padded /
+        // cropped points all fall into ONE cell per sample with r = 0, the smallest possible key: a plain
+        // store is enough for them and avoids ~10^5 serialised atomics on a single address.
+        unsigned* slot = p.cellmin + (size_t)b * p.H * p.W + cell;
+        const unsigned key = __float_as_uint(r);
+        if (key == 0u) *slot = 0u;
+        else atomicMin(slot, key);
         if (p.out_points != nullptr) {
             float* o = p.out_points + (size_t)i * 3;
             o[0] = x; o[1] = y; o[2] = z;
@@ -174,6 +179,7 @@ struct PoseParams {
 };
 
 constexpr int POSE_THREADS = 256;
+constexpr int POSE_PT = 8;          // points per thread; a CTA covers 4 * POSE_PT = 32 points
 
 __global__ void __launch_bounds__(POSE_THREADS) pose_head_kernel(const PoseParams p)
 {
@@ -183,23 +189,35 @@ __global__ void __launch_bounds__(POSE_THREADS) pose_head_kernel(const PoseParam
     const int b = blockIdx.y, gidx = blockIdx.x;
     const int c = threadIdx.x & 63, sub = threadIdx.x >> 6;
 
-    // online masked softmax over this CTA's slice of the points, per channel
+    // online masked softmax over this CTA's slice of the points, per channel; the slice is short
+    // (<= 4 * POSE_PT points) and all of a thread's loads are issued before any of them is used
     const int per = (p.N + p.G - 1) / p.G;
     const int n0 = gidx * per, n1 = min(p.N, n0 + per);
-    float m = -INFINITY, s = 0.f, a = 0.f;
-    for (int n = n0 + sub; n < n1; n += 4) {
-        const float* xyz = p.xyz + ((size_t)b * p.N + n) * 3;
-        if (__ldg(xyz) == 0.f && __ldg(xyz + 1) == 0.f && __ldg(xyz + 2) == 0.f) continue;
-        const float w = __ldg(p.weight + ((size_t)b * p.N + n) * 64 + c);
-        const float f = __ldg(p.feature + ((size_t)b * p.N + n) * 64 + c);
-        if (w > m) {
-            const float sc = expf(m - w);
-            s *= sc; a *= sc; m = w;
+    float wv[POSE_PT], fv[POSE_PT];
+    bool ok[POSE_PT];
+#pragma unroll
+    for (int i = 0; i < POSE_PT; ++i) {
+        const int n = n0 + sub + 4 * i;
+        ok[i] = n < n1;
+        wv[i] = 0.f; fv[i] = 0.f;
+        if (ok[i]) {
+            const float* xyz = p.xyz + ((size_t)b * p.N + n) * 3;
+            ok[i] = !(__ldg(xyz) == 0.f && __ldg(xyz + 1) == 0.f && __ldg(xyz + 2) == 0.f);
+            wv[i] = __ldg(p.weight + ((size_t)b * p.N + n) * 64 + c);
+            fv[i] = __ldg(p.feature + ((size_t)b * p.N + n) * 64 + c);
         }
-        const float e = expf(w - m);
-        s += e;
-        a = fmaf(e, f, a);
     }
+    float m = -INFINITY, s = 0.f, a = 0.f;
+#pragma unroll
+    for (int i = 0; i < POSE_PT; ++i)
+        if (ok[i]) m = fmaxf(m, wv[i]);
+#pragma unroll
+    for (int i = 0; i < POSE_PT; ++i)
+        if (ok[i]) {
+            const float e = expf(wv[i] - m);
+            s += e;
+            a = fmaf(e, fv[i], a);
+        }
     s_m[sub][c] = m; s_s[sub][c] = s; s_a[sub][c] = a;
     __syncthreads();
     if (sub == 0) {
@@ -224,8 +242,10 @@ __global__ void __launch_bounds__(POSE_THREADS) pose_head_kernel(const PoseParam
     if (threadIdx.x < 64) {
         const float* part = p.partial + (size_t)b * p.G * 192;
         float M = -INFINITY;
+#pragma unroll 8
         for (int g = 0; g < p.G; ++g) M = fmaxf(M, __ldcg(part + g * 192 + c));
         float S = 0.f, A = 0.f;
+#pragma unroll 4
         for (int g = 0; g < p.G; ++g) {
             const float mg = __ldcg(part + g * 192 + c);
             const float sc = mg == -INFINITY ? 0.f : expf(mg - M);
@@ -242,6 +262,7 @@ __global__ void __launch_bounds__(POSE_THREADS) pose_head_kernel(const PoseParam
     {   // conv1d 64 -> 256, no activation (pwclo_model.py:197); dropout is the identity at inference
         const int o = threadIdx.x;
         float acc = __ldg(p.b_big + o);
+#pragma unroll 16
         for (int k = 0; k < 64; ++k) acc = fmaf(s_pool[k], __ldg(p.w_big + k * 256 + o), acc);
         s_big[o] = acc;
     }
@@ -287,6 +308,33 @@ __global__ void __launch_bounds__(POSE_THREADS) pose_head_kernel(const PoseParam
     }
 }
 
+// Strided xyz pyramid (pwclo_model.py:88-114): level l keeps pixel (i*sh_l, j*sw_l) of the input image.
+struct PyramidParams {
+    int S, H, W;
+    int oh[4], ow[4], sh[4], sw[4];
+    long long start[5];          // first cell of each level in the flat work list (per sample)
+    const float* in;
+    float* out[4];
+};
+
+__global__ void pyramid_xyz_kernel(const PyramidParams p)
+{
+    const long long per = p.start[4];
+    const long long total = per * p.S;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int s = (int)(i / per);
+        const long long r = i - (long long)s * per;
+        int l = 0;
+        while (l < 3 && r >= p.start[l + 1]) ++l;
+        const int cell = (int)(r - p.start[l]);
+        const int y = cell / p.ow[l], x = cell - y * p.ow[l];
+        const float* src = p.in + (((size_t)s * p.H + (size_t)y * p.sh[l]) * p.W + (size_t)x * p.sw[l]) * 3;
+        float* dst = p.out[l] + ((size_t)s * p.oh[l] * p.ow[l] + cell) * 3;
+        dst[0] = __ldg(src); dst[1] = __ldg(src + 1); dst[2] = __ldg(src + 2);
+    }
+}
+
 __global__ void gt_pose_kernel(int B, const float* T_gt, const float* T_trans, const float* T_trans_inv,
                                const int* aug_frame, float* q_gt, float* t_gt)
 {
@@ -316,6 +364,32 @@ __global__ void gt_pose_kernel(int B, const float* T_gt, const float* T_trans, c
 }  // namespace elo
 
 using namespace elo;
+
+extern "C" int elo_pyramid_xyz(int samples, int H, int W, const int* out_h, const int* out_w, const int* stride_h,
+                               const int* stride_w, const float* xyz_in, float* const* out, void* stream)
+{
+    if (samples < 0 || H <= 0 || W <= 0 || !out_h || !out_w || !stride_h || !stride_w || !xyz_in || !out)
+        return set_error(ELO_ERR_INVALID_ARGUMENT, "pyramid_xyz: bad arguments");
+    if (samples == 0) return ELO_OK;
+    PyramidParams p;
+    p.S = samples; p.H = H; p.W = W; p.in = xyz_in;
+    p.start[0] = 0;
+    for (int l = 0; l < 4; ++l) {
+        if (out_h[l] <= 0 || out_w[l] <= 0 || stride_h[l] <= 0 || stride_w[l] <= 0 || !out[l] ||
+            (long long)(out_h[l] - 1) * stride_h[l] >= H || (long long)(out_w[l] - 1) * stride_w[l] >= W)
+            return set_error(ELO_ERR_INVALID_ARGUMENT, "pyramid_xyz: level outside the input image");
+        p.oh[l] = out_h[l]; p.ow[l] = out_w[l]; p.sh[l] = stride_h[l]; p.sw[l] = stride_w[l]; p.out[l] = out[l];
+        p.start[l + 1] = p.start[l] + (long long)out_h[l] * out_w[l];
+    }
+    const long long total = p.start[4] * samples;
+    long long blocks = (total + 255) / 256;
+    const long long cap = (long long)device_info().sm_count * 8;
+    if (blocks > cap) blocks = cap;
+    pyramid_xyz_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(p);
+    count_launches(1);
+    cudaError_t err = cudaGetLastError();
+    return err == cudaSuccess ? ELO_OK : set_cuda_error(err, "pyramid_xyz launch");
+}
 
 extern "C" int elo_gt_pose(int batch_size, const float* T_gt, const float* T_trans, const float* T_trans_inv,
                            const int* aug_frame, float* q_gt, float* t_gt, void* stream)
@@ -373,6 +447,8 @@ extern "C" int elo_pose_head(const elo_pose_head_desc* d, void* stream)
                    !d->q_norm_out || (d->has_coarse && (!d->q_coarse || !d->t_coarse)))))
         return set_error(ELO_ERR_INVALID_ARGUMENT, "pose_head: bad arguments");
     if (d->batch_size == 0) return ELO_OK;
+    if ((long long)d->num_slices * 4 * POSE_PT < d->num_points)
+        return set_error(ELO_ERR_INVALID_ARGUMENT, "pose_head: num_slices must be at least ceil(num_points / 32)");
     PoseParams p;
     p.B = d->batch_size; p.N = d->num_points; p.G = d->num_slices; p.has_coarse = d->has_coarse;
     p.feature = d->feature; p.weight = d->weight; p.xyz = d->xyz;

@@ -26,6 +26,7 @@ struct SmallParams {
     const float* weights;  // W1[(3+CF)][C1], b1[C1], W2[C1][C2], b2[C2], W3[C2][C3], b3[C3]  (BN folded)
     float* out;            // (B, n, C3)
     int* dbg_nbr;          // optional (B, n, K)
+    const int* nbr_in;     // optional (B, n, K) from elo_multi_search: skip the search
 };
 
 template <int CIN, int COUT>
@@ -69,7 +70,7 @@ __global__ void __launch_bounds__(256) set_conv_small_kernel(const SmallParams p
 
     const Window g = p.g;
     for (int i = threadIdx.x; i < NW; i += blockDim.x) wts[i] = __ldg(p.weights + i);
-    build_offsets(off, p.random_hw[blockIdx.y], g.kt, g.kH, g.kW);
+    build_offsets(off, p.random_hw[blockIdx.y], g.kt, g.kH, g.kW, blockDim.x);
     __syncthreads();
     const float* W1 = wts;
     const float* b1 = W1 + CIN * C1;
@@ -85,7 +86,8 @@ __global__ void __launch_bounds__(256) set_conv_small_kernel(const SmallParams p
     const long long q_base = p.q_base[blockIdx.y], q_end = q_base + p.per_set;
     const int sub = lane / K, kk = lane % K;
 
-    for (long long grp = (long long)blockIdx.x * 8 + warp; grp < groups; grp += (long long)gridDim.x * 8) {
+    const int nwarps = blockDim.x >> 5;
+    for (long long grp = (long long)blockIdx.x * nwarps + warp; grp < groups; grp += (long long)gridDim.x * nwarps) {
         nbr[lane] = -1;
         float cx[QPW], cy[QPW], cz[QPW];
         int cb[QPW];
@@ -102,6 +104,10 @@ __global__ void __launch_bounds__(256) set_conv_small_kernel(const SmallParams p
             const float* c = p.xyz + ((size_t)b * p.qs.H1 * p.qs.W1 + (size_t)h * p.qs.W1 + w) * 3;
             cx[qi] = __ldg(c); cy[qi] = __ldg(c + 1); cz[qi] = __ldg(c + 2);
             cb[qi] = b;
+            if (p.nbr_in != nullptr) {
+                if (lane < K) nbr[qi * K + lane] = __ldg(p.nbr_in + gq * K + lane);
+                continue;
+            }
             if (fmaxf(sq3(cx[qi], cy[qi], cz[qi]), 1e-10f) <= 1e-10f) continue;     // empty centre: all masked
             int* row = nbr + qi * K;
             auto emit = [&](int slot, int hh, int ww) { row[slot] = hh * g.w2 + ww; };
@@ -176,15 +182,20 @@ static int launch_small(const SmallParams& p, int nsets, cudaStream_t st)
     const size_t smem = ((NW * 4 + 15) & ~15) + (((size_t)p.g.kt * 8 + 15) & ~15) + 1024;
     constexpr int QPW = 32 / K;
     const long long groups = (p.per_set + QPW - 1) / QPW;
-    long long ctas = (groups + 7) / 8;
-    const long long cap = (long long)device_info().sm_count * 4 / nsets;
+    // few queries: fewer warps per CTA so that the work spreads over all SMs (each CTA re-reads the
+    // <= 17 KB of weights from L2, which is cheap); many queries: 8 warps, grid-stride
+    const long long sms = device_info().sm_count;
+    long long wpc = (groups * nsets + 2 * sms - 1) / (2 * sms);
+    wpc = wpc < 1 ? 1 : (wpc > 8 ? 8 : wpc);
+    long long ctas = (groups + wpc - 1) / wpc;
+    const long long cap = sms * 4 / nsets;
     if (ctas > cap) ctas = cap;
     auto kern = set_conv_small_kernel<CF, C1, C2, C3, K>;
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return set_cuda_error(e, "set_conv_small smem");
     }
-    kern<<<dim3((unsigned)ctas, nsets), 256, smem, st>>>(p);
+    kern<<<dim3((unsigned)ctas, nsets), (unsigned)wpc * 32, smem, st>>>(p);
     count_launches(1);
     cudaError_t err = cudaGetLastError();
     return err == cudaSuccess ? ELO_OK : set_cuda_error(err, "set_conv_small launch");
@@ -225,7 +236,7 @@ extern "C" int elo_set_conv_small(const elo_group_mlp_desc* d, void* stream)
         p.q_base[s] = (long long)d->set_batch_offset[u] * p.qs.oh * p.qs.ow;
     }
     p.xyz = d->xyz1; p.feat = d->feat2[0]; p.weights = d->weights[0];
-    p.out = d->out[0]; p.dbg_nbr = d->dbg_nbr[0];
+    p.out = d->out[0]; p.dbg_nbr = d->dbg_nbr[0]; p.nbr_in = d->nbr[0];
     cudaStream_t st = (cudaStream_t)stream;
     const int cf = d->feat_channels, c1 = d->cout[0], c2 = d->cout[1], c3 = d->cout[2], K = w->K;
     if (cf == 3 && c1 == 8 && c2 == 8 && c3 == 16 && K == 32) return launch_small<3, 8, 8, 16, 32>(p, d->nsets, st);

@@ -38,7 +38,7 @@ class PWCLOEngine:
         with torch.cuda.device(self.device):
             self.stream.wait_stream(torch.cuda.current_stream(self.device))
             with torch.cuda.stream(self.stream):
-                for _ in range(2):
+                for _ in range(2 if self.use_graph else 3):
                     self.outputs = self._forward()
             self.stream.synchronize()
             if self.use_graph:

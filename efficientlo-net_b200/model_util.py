@@ -47,6 +47,24 @@ def get_selected_idx(array, stride_h, stride_w, out_h, out_w):
     return SelectedIdx(array.shape[0], stride_h, stride_w, out_h, out_w, array.device)
 
 
+def xyz_pyramid(xyz_in, out_hs, out_ws, strides_h, strides_w):
+    """The four strided xyz grids of pwclo_model.py:88-114 in one launch.  strides are cumulative with
+    respect to xyz_in (S,H,W,3).  Returns a list of (S, out_h[l], out_w[l], 3) tensors."""
+    import ctypes
+    _lib.require_cuda("xyz_pyramid", xyz_in)
+    S, H, W, _ = xyz_in.shape
+    dev = xyz_in.device
+    xyz_in = xyz_in.contiguous().float()
+    outs = [torch.empty((S, h, w, 3), dtype=torch.float32, device=dev) for h, w in zip(out_hs, out_ws)]
+    arr = lambda v: (ctypes.c_int * 4)(*[int(x) for x in v])
+    ptrs = (ctypes.c_void_p * 4)(*[o.data_ptr() for o in outs])
+    with torch.cuda.device(dev):
+        rc = _lib.lib().elo_pyramid_xyz(S, H, W, arr(out_hs), arr(out_ws), arr(strides_h), arr(strides_w),
+                                        xyz_in.data_ptr(), ptrs, _lib.stream_ptr(dev))
+    _lib.check(rc, "elo_pyramid_xyz")
+    return outs
+
+
 # ---- spherical projection --------------------------------------------------------------------------
 def projection_constants(H_input, W_input):
     """The fp32 constants of model_util.py:189-210 (float64 python arithmetic, then float32)."""
@@ -122,8 +140,8 @@ def pose_head_call(feature_bnc, weight_bnc, xyz_bn3, heads=None, coarse=None, wa
         raise NotImplementedError("softmax_valid kernel is built for 64 channels")
     dev = feature_bnc.device
     f, w, x = feature_bnc.contiguous().float(), weight_bnc.contiguous().float(), xyz_bn3.contiguous().float()
-    G = max(1, min(64, (N + 63) // 64))
-    partial = _scratch("pose_partial", (B, 64, 192), torch.float32, dev)
+    G = (N + 31) // 32
+    partial = _scratch("pose_partial", (B, G, 192), torch.float32, dev)
     counter = _scratch("pose_counter", (B,), torch.int32, dev, fill=0)
     out = {}
     d = _lib.PoseHeadDesc()

@@ -7,8 +7,8 @@ CHUNK_FLOATS = 2048
 
 
 def pack_stream(P, scopes):
-    """Chunked stream for the shared-memory GEMM engine: per layer, row 0 = folded bias, rows 1..Cin =
-    W'[k][:], zero rows up to a multiple of 2048 / Cout; layers back to back in execution order."""
+    """Chunked stream for the shared-memory GEMM engine: per layer, rows 0..Cin-1 = W'[k][:], row Cin =
+    folded bias, zero rows up to a multiple of 2048 / Cout; layers back to back in execution order."""
     parts = []
     for scope in scopes:
         w, b = fold_bn(P, scope)
@@ -19,8 +19,8 @@ def pack_stream(P, scopes):
         rows = cin + 1
         padded = (rows + rows_per_chunk - 1) // rows_per_chunk * rows_per_chunk
         block = torch.zeros(padded, cout, dtype=torch.float32)
-        block[0] = b.float()
-        block[1:rows] = w.float()
+        block[:cin] = w.float()
+        block[cin] = b.float()
         parts.append(block.reshape(-1))
     return torch.cat(parts).contiguous()
 

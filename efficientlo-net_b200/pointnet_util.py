@@ -84,8 +84,46 @@ def _f32(t):
 
 
 # ----------------------------------------------------------------------------------------------
+def search_spec(select, xyz1, xyz2, queries, kernel_size, K, distance, stride_h, stride_w, random_hw, out=None):
+    """One entry for multi_search.  queries = (out_h, out_w, q_stride_h, q_stride_w) inside xyz1's image;
+    `out` an optional pre-allocated (B, out_h*out_w, K) int32 view to write into."""
+    return dict(select=select, xyz1=xyz1, xyz2=xyz2, queries=queries, kernel_size=kernel_size, K=K,
+                distance=distance, stride_h=stride_h, stride_w=stride_w, random_hw=random_hw, out=out)
+
+
+def multi_search(specs):
+    """Run up to 16 independent projection-aware neighbour searches in ONE launch (elo_multi_search).
+    Returns one (B, n, K) int32 table per spec: linear cell of the searched grid, -1 = masked slot."""
+    n = len(specs)
+    arr = (_lib.SearchDesc * n)()
+    outs, keep = [], []
+    dev = specs[0]["xyz1"].device
+    for i, sp in enumerate(specs):
+        xyz1, xyz2 = _f32(sp["xyz1"]), _f32(sp["xyz2"])
+        _lib.require_cuda("multi_search", xyz1, xyz2)
+        B, H, W, _ = xyz1.shape
+        oh, ow, qsh, qsw = sp["queries"]
+        kt = sp["kernel_size"][0] * sp["kernel_size"][1]
+        perm = _perm(sp["random_hw"], kt, dev)
+        out = sp["out"] if sp["out"] is not None else torch.empty((B, oh * ow, sp["K"]), dtype=torch.int32, device=dev)
+        if not out.is_contiguous() or out.dtype != torch.int32:
+            raise ValueError("multi_search: out must be a contiguous int32 tensor")
+        d = arr[i]
+        d.select, d.batch_size = int(bool(sp["select"])), B
+        d.queries = _lib.Queries(H, W, oh, ow, qsh, qsw)
+        d.window = _window(sp["kernel_size"], sp["K"], sp["distance"], sp["stride_h"], sp["stride_w"],
+                           xyz2.shape[1], xyz2.shape[2], perm)
+        d.xyz1, d.xyz2, d.out_nbr = xyz1.data_ptr(), xyz2.data_ptr(), out.data_ptr()
+        outs.append(out)
+        keep += [xyz1, xyz2, perm]
+    with torch.cuda.device(dev):
+        rc = _lib.lib().elo_multi_search(arr, n, _lib.stream_ptr(dev))
+    _lib.check(rc, "elo_multi_search")
+    return outs
+
+
 def set_conv(xyz_proj, points_proj, sel, K_sample, kernel_size, distance, layer_scopes, store, random_hws,
-             feat_channels=None, set_batch_offsets=(0,), debug=None):
+             feat_channels=None, set_batch_offsets=(0,), debug=None, nbr=None):
     """Set-conv kernel launch shared by down_conv and the batched pyramid of pwclo_model.
 
     xyz_proj (Bt, H, W, 3), points_proj (Bt, H, W, C) or None (zero features); ``sel`` a SelectedIdx
@@ -129,6 +167,7 @@ def set_conv(xyz_proj, points_proj, sel, K_sample, kernel_size, distance, layer_
         d.weights[s] = weights.data_ptr()
         d.out[s] = out.data_ptr()
         d.dbg_nbr[s] = _lib.ptr(dbg)
+        d.nbr[s] = _lib.ptr(nbr)
     _lib.call("elo_group_mlp_max" if big else "elo_set_conv_small", d, dev)
     if debug is not None:
         debug["nbr"] = dbg
@@ -157,7 +196,7 @@ def down_conv(xyz_proj, points_proj, selected_idx, K_sample, kernel_size, distan
 
 # ----------------------------------------------------------------------------------------------
 def up_conv_group(xyz1_proj, xyz2_proj, feat2_projs, kernel_size, stride_h, stride_w, nsample, distance,
-                  scopes_per_set, store, random_hws, debug=None):
+                  scopes_per_set, store, random_hws, debug=None, nbrs=None):
     """First half of set-upconv for one or two parameter sets in one launch: random-K (with stride)
     neighbours of every dense pixel in the sparse grid, [xyz_diff, feat2] -> up_1_* -> * mask -> max."""
     _lib.require_cuda("up_conv", xyz1_proj, xyz2_proj, *feat2_projs)
@@ -191,6 +230,7 @@ def up_conv_group(xyz1_proj, xyz2_proj, feat2_projs, kernel_size, stride_h, stri
         d.weights[s] = streams[u].data_ptr()
         d.out[s] = outs[u].data_ptr()
         d.dbg_nbr[s] = _lib.ptr(dbgs[u])
+        d.nbr[s] = _lib.ptr(nbrs[u]) if nbrs is not None else None
     _lib.call("elo_group_mlp_max", d, dev)
     if debug is not None:
         debug["nbr"] = dbgs
@@ -260,7 +300,8 @@ def up_conv(xyz1_proj, xyz2_proj, feat1_proj, feat2_proj, kernel_size, stride_h,
 # ----------------------------------------------------------------------------------------------
 def cost_volume(warped_xyz1_proj, xyz2_proj, points1_proj, points2_proj, kernel_size1, kernel_size2, nsample,
                 nsample_q, distance, mlp1, mlp2, is_training, bn_decay, scope, bn=True, pooling='max', knn=True,
-                corr_func='elementwise_product', random_hw_q=None, random_hw_p=None, params=None, debug=None):
+                corr_func='elementwise_product', random_hw_q=None, random_hw_p=None, params=None, debug=None,
+                nbr_q=None, nbr_p=None):
     """Two-stage attentive cost volume (utils/pointnet_util.py:33-149).  Stage 1 correlates every
     (warped) frame-1 pixel with its nsample_q nearest frame-2 pixels inside kernel_size2 (select-K,
     distance fixed at 1000 as in :51); stage 2 aggregates the stage-1 embeddings of nsample frame-1
@@ -294,6 +335,7 @@ def cost_volume(warped_xyz1_proj, xyz2_proj, points1_proj, points2_proj, kernel_
     d.weights_1, d.weights_2 = w1.data_ptr(), w2.data_ptr()
     d.stage1_out, d.out = stage1.data_ptr(), out.data_ptr()
     d.dbg_nbr_q, d.dbg_nbr_p = _lib.ptr(dq), _lib.ptr(dp)
+    d.nbr_q, d.nbr_p = _lib.ptr(nbr_q), _lib.ptr(nbr_p)
     _lib.call("elo_cost_volume_1", d, dev)
     _lib.call("elo_cost_volume_2", d, dev)
     if debug is not None:

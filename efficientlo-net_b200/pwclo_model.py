@@ -94,22 +94,49 @@ def get_model(point_cloud, H_input, W_input, T_gt, T_trans, T_trans_inv, is_trai
             K["xyz_f1_proj"], K["xyz_f2_proj"] = xyz_in[:B], xyz_in[B:]
 
         # ---- strided xyz pyramid (:88-114): pure slicing of the range image
-        xyz = [None] * 4
-        cur = xyz_in[:, ::STRIDE_H[1], ::STRIDE_W[1]]
+        csh, csw, ch, cw = [], [], STRIDE_H[1], STRIDE_W[1]
         for l in range(4):
-            cur = cur[:, ::STRIDE_H[l + 2], ::STRIDE_W[l + 2]][:, :oh[l + 2], :ow[l + 2]].contiguous()
-            xyz[l] = cur                                                        # (2B, oh, ow, 3)
+            ch, cw = ch * STRIDE_H[l + 2], cw * STRIDE_W[l + 2]
+            csh.append(ch)
+            csw.append(cw)
+        xyz = mu.xyz_pyramid(xyz_in, oh[2:], ow[2:], csh, csw)                  # 4 x (2B, oh, ow, 3)
+
+        # ---- every neighbour search that only needs the un-warped xyz pyramid, in ONE launch: the 8
+        # set-convs of the siamese pyramid, the initial cost volume's two, and new_layer3's.
+        sels = [pu.SelectedIdx(B, STRIDE_H[l + 2] * (STRIDE_H[1] if l == 0 else 1),
+                               STRIDE_W[l + 2] * (STRIDE_W[1] if l == 0 else 1), oh[l + 2], ow[l + 2], dev)
+                for l in range(4)]
+        sel3 = pu.SelectedIdx(B, STRIDE_H[5], STRIDE_W[5], oh[5], ow[5], dev)
+        grids = [xyz_in] + xyz[:3]                                              # grid searched by layer l
+        specs, nbr_pyr = [], []
+        for l in range(4):
+            K_l, ks = DOWN_CFG[l]
+            table = torch.empty((2 * B, oh[l + 2] * ow[l + 2], K_l), dtype=torch.int32, device=dev)
+            nbr_pyr.append(table)
+            for f, half in (("f1", slice(0, B)), ("f2", slice(B, 2 * B))):
+                g_ = grids[l][half]
+                specs.append(pu.search_spec(False, g_, g_, (sels[l].out_h, sels[l].out_w, sels[l].stride_h,
+                                                            sels[l].stride_w), ks, K_l, DOWN_CONV_DIS[l], 1, 1,
+                                            perms["sa1/layer%d/%s" % (l, f)], out=table[half]))
+        x2f1, x2f2 = xyz[2][:B], xyz[2][B:]
+        all2 = (oh[4], ow[4], 1, 1)
+        specs.append(pu.search_spec(True, x2f1, x2f2, all2, (5, 35), 32, 1000.0, 1, 1, perms["flow_embedding_l2_origin/q"]))
+        specs.append(pu.search_spec(False, x2f1, x2f1, all2, (3, 5), 4, COST_VOLUME_DIS[2], 1, 1,
+                                    perms["flow_embedding_l2_origin/p"]))
+        specs.append(pu.search_spec(False, x2f1, x2f1, (sel3.out_h, sel3.out_w, sel3.stride_h, sel3.stride_w), (5, 9),
+                                    16, DOWN_CONV_DIS[3], 1, 1, perms["new_layer3"]))
+        tables = pu.multi_search(specs)
+        nbr_l2o_q, nbr_l2o_p, nbr_new3 = tables[8], tables[9], tables[10]
 
         # ---- siamese feature pyramid (:117-165): frames share weights, each call its own scan order
         pts = [None] * 4
         src_xyz, src_pts, src_c = xyz_in, None, 3
         for l in range(4):
-            sel = pu.SelectedIdx(B, STRIDE_H[l + 2] * (STRIDE_H[1] if l == 0 else 1),
-                                 STRIDE_W[l + 2] * (STRIDE_W[1] if l == 0 else 1), oh[l + 2], ow[l + 2], dev)
+            sel = sels[l]
             scopes = ["sa1/layer%d/conv%d" % (l, j) for j in range(3)]
             feat = pu.set_conv(src_xyz, src_pts, sel, DOWN_CFG[l][0], DOWN_CFG[l][1], DOWN_CONV_DIS[l], scopes, store,
                                [perms["sa1/layer%d/f1" % l], perms["sa1/layer%d/f2" % l]], feat_channels=src_c,
-                               set_batch_offsets=(0, B))
+                               set_batch_offsets=(0, B), nbr=nbr_pyr[l])
             pts[l] = feat                                                       # (2B, n_l, C_l)
             src_xyz, src_pts, src_c = xyz[l], feat.view(2 * B, oh[l + 2], ow[l + 2], -1), feat.shape[-1]
             if want:
@@ -128,10 +155,9 @@ def get_model(point_cloud, H_input, W_input, T_gt, T_trans, T_trans_inv, is_trai
         l2_new = pu.cost_volume(f1(xyz[2]), f2(xyz[2]), grid(2, f1(pts[2])), grid(2, f2(pts[2])), [3, 5], [5, 35],
                                 4, 32, COST_VOLUME_DIS[2], [128, 64, 64], [128, 64], False, bn_decay,
                                 "flow_embedding_l2_origin", random_hw_q=perms["flow_embedding_l2_origin/q"],
-                                random_hw_p=perms["flow_embedding_l2_origin/p"])
-        sel3 = pu.SelectedIdx(B, STRIDE_H[5], STRIDE_W[5], oh[5], ow[5], dev)
+                                random_hw_p=perms["flow_embedding_l2_origin/p"], nbr_q=nbr_l2o_q, nbr_p=nbr_l2o_p)
         l3_cv = pu.set_conv(f1(xyz[2]), grid(2, l2_new), sel3, 16, (5, 9), DOWN_CONV_DIS[3],
-                            ["new_layer3/conv%d" % j for j in range(3)], store, [perms["new_layer3"]])
+                            ["new_layer3/conv%d" % j for j in range(3)], store, [perms["new_layer3"]], nbr=nbr_new3)
         # ---- level 3: embedding mask, attention pooling, coarse pose (:181-208)
         l3_w = pu.flow_predictor(f1(pts[3]), None, l3_cv, [128, 64], False, bn_decay, "l3_costvolume_predict_ww")
         l3_xyz = f1(xyz[3]).reshape(B, -1, 3)
@@ -150,16 +176,26 @@ def get_model(point_cloud, H_input, W_input, T_gt, T_trans, T_trans_inv, is_trai
             # warp with the coarse pose and re-project (:213-237): one fused pass
             xyz_wp, pts_wp, warped = mu.project_points(f1(xyz[lvl]).reshape(B, -1, 3), f1(pts[lvl]), h, w_, mode=2,
                                                        q=q, t=t, want_points=want)
+            # the level's four neighbour searches (cost volume q / p, the two up-convs) in one launch
+            names = ["up_sa_layer_layer_l%dw" % lvl, "up_sa_layer_layer_l%dcostvolume" % lvl]
+            allq = (h, w_, 1, 1)
+            s_h, s_w = STRIDE_H[lvl + 3], STRIDE_W[lvl + 3]
+            nq_, np_, nu0, nu1 = pu.multi_search([
+                pu.search_spec(True, xyz_wp, f2(xyz[lvl]), allq, CV_KERNEL_Q[lvl], 6, 1000.0, 1, 1,
+                               perms["flow_embedding_l%d/q" % lvl]),
+                pu.search_spec(False, xyz_wp, xyz_wp, allq, (3, 5), 4, COST_VOLUME_DIS[lvl], 1, 1,
+                               perms["flow_embedding_l%d/p" % lvl]),
+                pu.search_spec(False, xyz_wp, up_xyz, allq, (7, 15), 8, UP_CONV_DIS[lvl], s_h, s_w, perms[names[0]]),
+                pu.search_spec(False, xyz_wp, up_xyz, allq, (7, 15), 8, UP_CONV_DIS[lvl], s_h, s_w, perms[names[1]])])
             # cost volume between the warped frame 1 and frame 2 (:242-244)
             cv = pu.cost_volume(xyz_wp, f2(xyz[lvl]), pts_wp, grid(lvl, f2(pts[lvl])), [3, 5], CV_KERNEL_Q[lvl], 4, 6,
                                 COST_VOLUME_DIS[lvl], [128, 64, 64], [128, 64], False, bn_decay,
                                 "flow_embedding_l%d" % lvl, random_hw_q=perms["flow_embedding_l%d/q" % lvl],
-                                random_hw_p=perms["flow_embedding_l%d/p" % lvl])
+                                random_hw_p=perms["flow_embedding_l%d/p" % lvl], nbr_q=nq_, nbr_p=np_)
             # the two set-upconvs of the level (:247-251) share one launch for their first half ...
-            names = ["up_sa_layer_layer_l%dw" % lvl, "up_sa_layer_layer_l%dcostvolume" % lvl]
-            ups = pu.up_conv_group(xyz_wp, up_xyz, [up_w, up_pred], (7, 15), STRIDE_H[lvl + 3], STRIDE_W[lvl + 3], 8,
+            ups = pu.up_conv_group(xyz_wp, up_xyz, [up_w, up_pred], (7, 15), s_h, s_w, 8,
                                    UP_CONV_DIS[lvl], [["%s/up_1_%d" % (n, j) for j in range(2)] for n in names],
-                                   store, [perms[n] for n in names])
+                                   store, [perms[n] for n in names], nbrs=[nu0, nu1])
             # ... and one launch for their second half chained into the two predictors (:253-254)
             rows = B * h * w_
             pts_w = pts_wp.reshape(rows, C)

@@ -64,9 +64,9 @@ int elo_fused_conv_random_k(int batch_size, int H, int W, int npoints, int kerne
  * reduce_max / softmax / reduce_sum).  Descriptors are plain C structs; tensors are fp32,
  * C-contiguous, channel-last, on the device.
  *
- * Weights are the packed stream efficientlo-net_b200/packing.py produces: per layer, row 0 = bias
- * with the inference batch-norm folded in, rows 1..Cin = W'[k][0..Cout), zero rows up to a multiple
- * of (2048 / Cout); layers back to back in execution order.
+ * Weights are the packed stream efficientlo-net_b200/packing.py produces: per layer, rows 0..Cin-1 =
+ * W'[k][0..Cout) and row Cin = bias, both with the inference batch-norm folded in, then zero rows up to
+ * a multiple of (2048 / Cout); layers back to back in execution order.
  */
 typedef struct {
     int kernel_size_H, kernel_size_W, K;
@@ -81,6 +81,22 @@ typedef struct {
     int out_h, out_w;            /* queries per sample: cells (i*q_stride_h, j*q_stride_w) */
     int q_stride_h, q_stride_w;  /* 1,1 = every pixel (get_hw_idx); >1 = strided centres (get_selected_idx) */
 } elo_queries;
+
+/* Batched neighbour search: nspec independent select-K / random-K searches in one launch, each writing
+ * the compact table the fused blocks take as `nbr`: out_nbr (B, out_h*out_w, K) int32 = linear cell
+ * (h * small_w + w) of the k-th selected neighbour in the searched grid, -1 where selected_mask is 0.
+ * Same selection, bit for bit, as elo_fused_conv_{select,random}_k with flag_copy = 0. */
+#define ELO_MAX_SEARCH 16
+typedef struct {
+    int select;               /* 1 = select-K, 0 = random-K */
+    int batch_size;
+    elo_queries queries;
+    elo_window window;
+    const float *xyz1;        /* (B, H, W, 3) query image */
+    const float *xyz2;        /* (B, small_h, small_w, 3) searched grid */
+    int *out_nbr;
+} elo_search_desc;
+int elo_multi_search(const elo_search_desc *specs, int nspec, void *stream);
 
 /* set-conv (utils/pointnet_util.py:179-250 down_conv, mlp2 = None) and the first half of set-upconv
  * (:254-298): random-K neighbours of each query in (xyz2, feat2); rows [q_k - p, feat2_k] -> 2..3
@@ -103,6 +119,7 @@ typedef struct {
     const float *weights[2];
     float *out[2];
     int *dbg_nbr[2];          /* optional (B, n, K): selected linear cell of the searched grid, -1 = masked */
+    const int *nbr[2];        /* optional: tables from elo_multi_search; when given, the kernel does not search */
 } elo_group_mlp_desc;
 int elo_group_mlp_max(const elo_group_mlp_desc *desc, void *stream);
 
@@ -123,6 +140,7 @@ typedef struct {
     float *stage1_out;        /* (B, H*W, 64) written by stage 1, read by stage 2 */
     float *out;               /* (B, H*W, 64) */
     int *dbg_nbr_q, *dbg_nbr_p;
+    const int *nbr_q, *nbr_p; /* optional: tables from elo_multi_search (stage 1 / stage 2) */
 } elo_cost_volume_desc;
 int elo_cost_volume_1(const elo_cost_volume_desc *desc, void *stream);
 int elo_cost_volume_2(const elo_cost_volume_desc *desc, void *stream);
@@ -196,6 +214,12 @@ typedef struct {
     float *q_out, *t_out, *q_norm_out, *pooled_out;
 } elo_pose_head_desc;
 int elo_pose_head(const elo_pose_head_desc *desc, void *stream);
+
+/* Strided xyz pyramid (pwclo_model.py:88-114, get_selected_idx + gather_nd): level l of 4 keeps pixel
+ * (i*stride_h[l], j*stride_w[l]) of xyz_in (samples,H,W,3) for i < out_h[l], j < out_w[l]; strides are
+ * cumulative with respect to xyz_in.  out: 4 device pointers (host array), (samples,out_h[l],out_w[l],3). */
+int elo_pyramid_xyz(int samples, int H, int W, const int *out_h, const int *out_w, const int *stride_h,
+                    const int *stride_w, const float *xyz_in, float *const *out, void *stream);
 
 /* Ground-truth pose as the network's (q, t) parametrisation (model_util.py:386-426): per sample
  * T = T_trans T_gt (aug_frame 2) or T_gt T_trans_inv (aug_frame 1); q from the zyx Euler angles of R,
