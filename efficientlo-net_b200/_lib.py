@@ -85,6 +85,7 @@ SIGNATURES = {
     "elo_row_mlp": [ctypes.POINTER(RowMlpDesc), _c_void_p],
     "elo_project": [ctypes.POINTER(ProjectDesc), _c_void_p],
     "elo_pose_head": [ctypes.POINTER(PoseHeadDesc), _c_void_p],
+    "elo_tc_dense_test": [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_void_p],
     "elo_pyramid_xyz": [_c_int, _c_int, _c_int, ctypes.POINTER(_c_int), ctypes.POINTER(_c_int),
                         ctypes.POINTER(_c_int), ctypes.POINTER(_c_int), _c_void_p, ctypes.POINTER(_c_void_p), _c_void_p],
     "elo_gt_pose": [_c_int, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p],
@@ -110,6 +111,10 @@ def lib():
         handle.elo_version.restype = _c_int
         handle.elo_launch_count.restype = _c_ll
         handle.elo_launch_count.argtypes = []
+        handle.elo_set_mlp_engine.argtypes = [_c_int]
+        handle.elo_set_mlp_engine.restype = _c_int
+        handle.elo_get_mlp_engine.argtypes = []
+        handle.elo_get_mlp_engine.restype = _c_int
         for name, argtypes in SIGNATURES.items():
             fn = getattr(handle, name)
             fn.argtypes = argtypes
@@ -141,6 +146,15 @@ def ptr(t):
 # on the launching stream and (name, tag, start, end) is appended.
 PROFILE = None
 PROFILE_TAG = [""]
+
+
+def mlp_engine():
+    """1 = tcgen05 tensor cores (3xTF32), 0 = fp32 FFMA."""
+    return int(lib().elo_get_mlp_engine())
+
+
+def set_mlp_engine(engine):
+    check(lib().elo_set_mlp_engine(int(engine)), "elo_set_mlp_engine")
 
 
 def launch_count():

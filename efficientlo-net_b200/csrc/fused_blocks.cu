@@ -17,6 +17,7 @@
 
 #include "../../include/elo_b200.h"
 #include "elo_common.cuh"
+#include "elo_tc_engine.cuh"
 #include "elo_tile.cuh"
 
 namespace elo {
@@ -388,7 +389,8 @@ struct RowMlpParams {
     int src_c[2][3];           // channels of each source
     int src_prev[2][3];        // 1: the source is the previous phase's output (kept in shared memory)
     int nl[2], cout[2][3];
-    int total_chunks, nring;
+    int total_chunks, nring, stage_ch;
+    int slot[2][3], stage_here[2][3];   // tensor-core path: staging channel of each source / stage it here
     const float* src[2][2][3]; // [set][phase][i]
     const float* weights[2];
     float* out[2];
@@ -465,6 +467,376 @@ __global__ void __launch_bounds__(LAUNCH_THREADS, 1) row_mlp_kernel(const RowMlp
         // copy-out above happens before any write, and the prev->X copy is fenced by the
         // __syncthreads() before the dense chain.
     }
+}
+
+// ================================================================================================
+// Tensor-core (tcgen05, 3xTF32) versions of the four kernels.  Same tiles, same search / gather /
+// pooling code; the layers run on the TcPipe engine (elo_tc_engine.cuh): activations in TMEM, weights
+// streamed by the TMA warp, MMAs issued by a dedicated warp.  Tiles have TC_ROWS = 128 rows.
+// `weights` here = [TC stream: total_chunks x 4096 floats][biases of all layers, in order].
+
+struct TcSmem {
+    float* ring; uint64_t* bars; uint32_t* tmem_holder; int2* off; int* nbr; float* ctr; float* X;
+};
+
+__device__ __forceinline__ TcSmem tc_carve(unsigned char* raw, int nring, int kt, size_t staging_floats)
+{
+    SmemCarver sc(raw);
+    TcSmem m;
+    m.ring = sc.take<float>((size_t)nring * TC_CHUNK_FLOATS);
+    m.bars = sc.take<uint64_t>(2 * MAX_RING + 2);
+    m.tmem_holder = sc.take<uint32_t>(4);
+    m.off = sc.take<int2>(kt);
+    m.nbr = sc.take<int>(TC_ROWS);
+    m.ctr = sc.take<float>(TC_ROWS * 4);
+    m.X = sc.take<float>(staging_floats);
+    return m;
+}
+
+__global__ void __launch_bounds__(TC_LAUNCH_THREADS, 1) group_mlp_max_tc_kernel(const GroupMlpParams p)
+{
+    constexpr int RS = TC_ROWS;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int cin0 = 3 + p.Cf;
+    const int cout_last = p.cout[p.nl - 1];
+    const int stage_ch = max((cin0 + 3) & ~3, cout_last);
+    TcSmem sm = tc_carve(smem_raw, p.nring, p.g.kt, (size_t)stage_ch * RS);
+    const int set = blockIdx.y, warp = threadIdx.x >> 5;
+    const Window g = p.g;
+    TcPipe pipe;
+    pipe.init(sm.ring, sm.bars, p.nring, sm.tmem_holder, p.weights[set] + (size_t)p.total_chunks * TC_CHUNK_FLOATS);
+    if (warp == COMPUTE_WARPS) { pipe.produce(p.weights[set], p.total_chunks); return; }
+    if (warp == COMPUTE_WARPS + 1) {
+        if ((threadIdx.x & 31) == 0) {
+            int cin = cin0;
+            for (int l = 0; l < p.nl; ++l) { pipe.issue_layer(0, cin, p.cout[l]); cin = p.cout[l]; }
+        }
+        return;
+    }
+    int* nbr = sm.nbr; float* ctr = sm.ctr; float* X = sm.X;
+    if (p.nbr_in[set] == nullptr) build_offsets(sm.off, p.random_hw[set], g.kt, g.kH, g.kW, CTA_THREADS);
+    for (int i = threadIdx.x; i < RS; i += CTA_THREADS) nbr[i] = -1;
+    compute_sync();
+    const long long q0 = p.q_base[set] + (long long)blockIdx.x * p.qt;
+    const long long total_q = p.q_end[set];
+    const int cells2 = g.h2 * g.w2;
+    if (p.nbr_in[set] != nullptr) tile_load_nbr(p.qs, g.K, p.xyz1, p.nbr_in[set], q0, p.qt, total_q, nbr, ctr);
+    else tile_search<false>(p.qs, g, p.xyz1, p.xyz2, sm.off, q0, p.qt, total_q, nbr, ctr, nullptr, nullptr);
+    compute_sync();
+    for (int r = threadIdx.x; r < RS; r += CTA_THREADS) {
+        const int q = r / g.K;
+        float dx = 0.f, dy = 0.f, dz = 0.f;
+        if (q < p.qt) {
+            const int b = __float_as_int(ctr[q * 4 + 3]);
+            if (b >= 0) {
+                float qx = 0.f, qy = 0.f, qz = 0.f;
+                const int cell = nbr[r];
+                if (cell >= 0) {
+                    const float* s = p.xyz2 + ((size_t)b * cells2 + cell) * 3;
+                    qx = __ldg(s); qy = __ldg(s + 1); qz = __ldg(s + 2);
+                }
+                dx = qx - ctr[q * 4 + 0]; dy = qy - ctr[q * 4 + 1]; dz = qz - ctr[q * 4 + 2];
+            }
+        }
+        X[act_index(0, r, RS)] = dx; X[act_index(1, r, RS)] = dy; X[act_index(2, r, RS)] = dz;
+    }
+    {
+        const int K = g.K, qt = p.qt;
+        gather_features(X, RS, 3, p.feat2[set], p.Cf, RS, [&](int r) -> long long {
+            const int q = r / K;
+            if (q >= qt || nbr[r] < 0) return -1;
+            return (long long)__float_as_int(ctr[q * 4 + 3]) * cells2 + nbr[r];
+        });
+    }
+    compute_sync();
+    pipe.load_a_from_smem(X, 0, cin0, 0);
+    pipe.signal_a_ready();
+    for (int l = 0; l < p.nl; ++l) {
+        const bool last = l == p.nl - 1;
+        pipe.epilogue<true>(p.cout[l], [&](int b, const float (&v)[16]) {
+            if (last) pipe.store_smem(X, 0, b, v);       // X is dead: every thread loaded its row before layer 0 ran
+            else pipe.store_a(0, b, v);
+        });
+        if (!last) pipe.signal_a_ready();
+    }
+    compute_sync();
+    float* out = p.out[set];
+    for (int t = threadIdx.x; t < p.qt * cout_last; t += CTA_THREADS) {
+        const int q = t / cout_last, c = t - q * cout_last;
+        const long long gq = q0 + q;
+        if (gq >= total_q) break;
+        float m = 0.f;
+        for (int k = 0; k < g.K; ++k)
+            if (nbr[q * g.K + k] >= 0) m = fmaxf(m, X[act_index(c, q * g.K + k, RS)]);
+        out[gq * cout_last + c] = m;
+    }
+    if (p.dbg_nbr[set] != nullptr)
+        for (int t = threadIdx.x; t < p.qt * g.K; t += CTA_THREADS)
+            if (q0 + t / g.K < total_q) p.dbg_nbr[set][q0 * g.K + t] = nbr[t];
+    pipe.finish();
+}
+
+__global__ void __launch_bounds__(TC_LAUNCH_THREADS, 1) cost_volume_1_tc_kernel(const Cv1Params p)
+{
+    constexpr int RS = TC_ROWS;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int C = p.C, xc = 10 + 2 * C;
+    const int stage_ch = max((xc + 3) & ~3, 128);
+    TcSmem sm = tc_carve(smem_raw, p.nring, p.g.kt, (size_t)stage_ch * RS);
+    const int warp = threadIdx.x >> 5;
+    const Window g = p.g;
+    TcPipe pipe;
+    pipe.init(sm.ring, sm.bars, p.nring, sm.tmem_holder, p.weights + (size_t)p.total_chunks * TC_CHUNK_FLOATS);
+    if (warp == COMPUTE_WARPS) { pipe.produce(p.weights, p.total_chunks); return; }
+    if (warp == COMPUTE_WARPS + 1) {
+        if ((threadIdx.x & 31) == 0) {
+            pipe.issue_layer(0, xc, 128);     // CV_0
+            pipe.issue_layer(0, 128, 64);     // CV_1
+            pipe.issue_layer(0, 64, 64);      // CV_2      -> F
+            pipe.issue_layer(0, 10, 64);      // CV_xyz    -> enc
+            pipe.issue_layer(0, 128, 128);    // sum_CV_0 on [enc | F]
+            pipe.issue_layer(0, 128, 64);     // sum_CV_1  -> logits
+        }
+        return;
+    }
+    int* nbr = sm.nbr; float* ctr = sm.ctr; float* X = sm.X;
+    for (int i = threadIdx.x; i < RS; i += CTA_THREADS) nbr[i] = -1;
+    compute_sync();
+    const long long q0 = (long long)blockIdx.x * p.qt;
+    const int cells = g.h2 * g.w2;
+    // this kernel takes its neighbour table from elo_multi_search (the launcher guarantees nbr_in)
+    tile_load_nbr(p.qs, g.K, p.xyz1, p.nbr_in, q0, p.qt, p.total_q, nbr, ctr);
+    compute_sync();
+    for (int r = threadIdx.x; r < RS; r += CTA_THREADS) {
+        const int q = r / g.K;
+        float px = 0.f, py = 0.f, pz = 0.f, qx = 0.f, qy = 0.f, qz = 0.f;
+        if (q < p.qt) {
+            const int b = __float_as_int(ctr[q * 4 + 3]);
+            if (b >= 0) {
+                px = ctr[q * 4 + 0]; py = ctr[q * 4 + 1]; pz = ctr[q * 4 + 2];
+                const int cell = nbr[r];
+                if (cell >= 0) {
+                    const float* s = p.xyz2 + ((size_t)b * cells + cell) * 3;
+                    qx = __ldg(s); qy = __ldg(s + 1); qz = __ldg(s + 2);
+                }
+            }
+        }
+        write_xyz10(X, RS, r, px, py, pz, qx, qy, qz);
+    }
+    {
+        const int K = g.K, qt = p.qt, nq = p.qs.oh * p.qs.ow;
+        const long long total = p.total_q;
+        gather_features(X, RS, 10, p.f1, C, RS, [&](int r) -> long long {
+            const int q = r / K;
+            return (q < qt && q0 + q < total) ? q0 + q : -1;
+        });
+        gather_features(X, RS, 10 + C, p.f2, C, RS, [&](int r) -> long long {
+            const int q = r / K;
+            if (q >= qt || nbr[r] < 0) return -1;
+            return (long long)((q0 + q) / nq) * cells + nbr[r];
+        });
+    }
+    compute_sync();
+    // the 10 xyz channels are needed again by CV_xyz after the tile's A region has been overwritten
+    float x10[16];
+    {
+        const int m = pipe.my_row();
+#pragma unroll
+        for (int i = 0; i < 16; ++i) x10[i] = i < 10 ? X[act_index(i, m, RS)] : 0.f;
+    }
+    pipe.load_a_from_smem(X, 0, xc, 0);
+    pipe.signal_a_ready();
+    float* S = X;                               // staging reused: F at channels [0,64), logits at [64,128)
+    pipe.epilogue<true>(128, [&](int b, const float (&v)[16]) { pipe.store_a(0, b, v); });        // CV_0
+    pipe.signal_a_ready();
+    pipe.epilogue<true>(64, [&](int b, const float (&v)[16]) { pipe.store_a(0, b, v); });         // CV_1
+    pipe.signal_a_ready();
+    pipe.epilogue<true>(64, [&](int b, const float (&v)[16]) {                                    // CV_2 = F
+        pipe.store_a(64, b, v);
+        pipe.store_smem(S, 0, b, v);
+    });
+    if (pipe.my_half() == 0) {                  // re-materialise the xyz block for CV_xyz
+        uint32_t hi[16], lo[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) tc::split_tf32(x10[i], hi[i], lo[i]);
+        tc::tmem_st16(pipe.my_lane_addr(), hi);
+        tc::tmem_st16(pipe.my_lane_addr() + TC_A_LO, lo);
+    }
+    pipe.signal_a_ready();
+    pipe.epilogue<true>(64, [&](int b, const float (&v)[16]) { pipe.store_a(0, b, v); });         // CV_xyz = enc
+    pipe.signal_a_ready();
+    pipe.epilogue<true>(128, [&](int b, const float (&v)[16]) { pipe.store_a(0, b, v); });        // sum_CV_0
+    pipe.signal_a_ready();
+    pipe.epilogue<true>(64, [&](int b, const float (&v)[16]) { pipe.store_smem(S, 64, b, v); });  // logits
+    compute_sync();
+    for (int t = threadIdx.x; t < p.qt * 64; t += CTA_THREADS) {
+        const int q = t >> 6, c = t & 63;
+        const long long gq = q0 + q;
+        if (gq >= p.total_q) break;
+        p.out[gq * 64 + c] = softmax_pool(S + 64 * RS, S, nbr + q * g.K, c, q * g.K, g.K, RS);
+    }
+    if (p.dbg_nbr != nullptr)
+        for (int t = threadIdx.x; t < p.qt * g.K; t += CTA_THREADS)
+            if (q0 + t / g.K < p.total_q) p.dbg_nbr[q0 * g.K + t] = nbr[t];
+    pipe.finish();
+}
+
+__global__ void __launch_bounds__(TC_LAUNCH_THREADS, 1) cost_volume_2_tc_kernel(const Cv2Params p)
+{
+    constexpr int RS = TC_ROWS;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int C = p.C;
+    // staging channels: [0,10) xyz, [16,16+C) f1, [16+C,80+C) stage-1 of the neighbour, [80+C,144+C) logits
+    TcSmem sm = tc_carve(smem_raw, p.nring, p.g.kt, (size_t)(144 + C) * RS);
+    const int warp = threadIdx.x >> 5;
+    const Window g = p.g;
+    TcPipe pipe;
+    pipe.init(sm.ring, sm.bars, p.nring, sm.tmem_holder, p.weights + (size_t)p.total_chunks * TC_CHUNK_FLOATS);
+    if (warp == COMPUTE_WARPS) { pipe.produce(p.weights, p.total_chunks); return; }
+    if (warp == COMPUTE_WARPS + 1) {
+        if ((threadIdx.x & 31) == 0) {
+            pipe.issue_layer(0, 10, 64);          // sum_xyz_encoding
+            pipe.issue_layer(0, 128 + C, 128);    // sum_cost_volume_0 on [enc | f1 | stage-1]
+            pipe.issue_layer(0, 128, 64);         // sum_cost_volume_1 -> logits
+        }
+        return;
+    }
+    int* nbr = sm.nbr; float* ctr = sm.ctr; float* X = sm.X;
+    for (int i = threadIdx.x; i < RS; i += CTA_THREADS) nbr[i] = -1;
+    compute_sync();
+    const long long q0 = (long long)blockIdx.x * p.qt;
+    const int cells = g.h2 * g.w2;
+    tile_load_nbr(p.qs, g.K, p.xyz1, p.nbr_in, q0, p.qt, p.total_q, nbr, ctr);
+    compute_sync();
+    for (int r = threadIdx.x; r < RS; r += CTA_THREADS) {
+        const int q = r / g.K;
+        float px = 0.f, py = 0.f, pz = 0.f, qx = 0.f, qy = 0.f, qz = 0.f;
+        if (q < p.qt) {
+            const int b = __float_as_int(ctr[q * 4 + 3]);
+            if (b >= 0) {
+                px = ctr[q * 4 + 0]; py = ctr[q * 4 + 1]; pz = ctr[q * 4 + 2];
+                const int cell = nbr[r];
+                if (cell >= 0) {
+                    const float* s = p.xyz1 + ((size_t)b * cells + cell) * 3;
+                    qx = __ldg(s); qy = __ldg(s + 1); qz = __ldg(s + 2);
+                }
+            }
+        }
+        write_xyz10(X, RS, r, px, py, pz, qx, qy, qz);
+    }
+    {
+        const int K = g.K, qt = p.qt, nq = p.qs.oh * p.qs.ow;
+        const long long total = p.total_q;
+        gather_features(X, RS, 16, p.f1, C, RS, [&](int r) -> long long {
+            const int q = r / K;
+            return (q < qt && q0 + q < total) ? q0 + q : -1;
+        });
+        gather_features(X, RS, 16 + C, p.cv1, 64, RS, [&](int r) -> long long {
+            const int q = r / K;
+            if (q >= qt || nbr[r] < 0) return -1;
+            return (long long)((q0 + q) / nq) * cells + nbr[r];
+        });
+    }
+    compute_sync();
+    pipe.load_a_from_smem(X, 0, 10, 0);
+    pipe.load_a_from_smem(X, 16, C + 64, 64);
+    pipe.signal_a_ready();
+    pipe.epilogue<true>(64, [&](int b, const float (&v)[16]) { pipe.store_a(0, b, v); });         // enc
+    pipe.signal_a_ready();
+    pipe.epilogue<true>(128, [&](int b, const float (&v)[16]) { pipe.store_a(0, b, v); });
+    pipe.signal_a_ready();
+    pipe.epilogue<true>(64, [&](int b, const float (&v)[16]) { pipe.store_smem(X, 80 + C, b, v); });
+    compute_sync();
+    for (int t = threadIdx.x; t < p.qt * 64; t += CTA_THREADS) {
+        const int q = t >> 6, c = t & 63;
+        const long long gq = q0 + q;
+        if (gq >= p.total_q) break;
+        const int* nrow = nbr + q * g.K;
+        float m = -INFINITY;
+        for (int k = 0; k < g.K; ++k)
+            m = fmaxf(m, nrow[k] >= 0 ? X[act_index(80 + C + c, q * g.K + k, RS)] : -1e10f);
+        float s = 0.f, acc = 0.f;
+        for (int k = 0; k < g.K; ++k) {
+            const float l = nrow[k] >= 0 ? X[act_index(80 + C + c, q * g.K + k, RS)] : -1e10f;
+            const float e = expf(l - m);
+            s += e;
+            acc = fmaf(e, X[act_index(16 + C + c, q * g.K + k, RS)], acc);
+        }
+        p.out[gq * 64 + c] = acc / s;
+    }
+    if (p.dbg_nbr != nullptr)
+        for (int t = threadIdx.x; t < p.qt * g.K; t += CTA_THREADS)
+            if (q0 + t / g.K < p.total_q) p.dbg_nbr[q0 * g.K + t] = nbr[t];
+    pipe.finish();
+}
+
+__global__ void __launch_bounds__(TC_LAUNCH_THREADS, 1) row_mlp_tc_kernel(const RowMlpParams p)
+{
+    constexpr int RS = TC_ROWS;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int set = blockIdx.y, warp = threadIdx.x >> 5;
+    TcSmem sm = tc_carve(smem_raw, p.nring, 0, (size_t)p.stage_ch * RS);
+    TcPipe pipe;
+    pipe.init(sm.ring, sm.bars, p.nring, sm.tmem_holder, p.weights[set] + (size_t)p.total_chunks * TC_CHUNK_FLOATS);
+    if (warp == COMPUTE_WARPS) { pipe.produce(p.weights[set], p.total_chunks); return; }
+    if (warp == COMPUTE_WARPS + 1) {
+        if ((threadIdx.x & 31) == 0)
+            for (int ph = 0; ph < p.nphase; ++ph) {
+                int cin = 0;
+                for (int i = 0; i < p.nsrc[ph]; ++i) cin += p.src_c[ph][i];
+                for (int l = 0; l < p.nl[ph]; ++l) { pipe.issue_layer(0, cin, p.cout[ph][l]); cin = p.cout[ph][l]; }
+            }
+        return;
+    }
+    float* X = sm.X;
+    const long long r0 = (long long)blockIdx.x * p.rt;
+    const long long rows = p.rows;
+    const int rt = p.rt;
+    for (int ph = 0; ph < p.nphase; ++ph)
+        for (int i = 0; i < p.nsrc[ph]; ++i) {
+            if (p.src_prev[ph][i] || !p.stage_here[ph][i]) continue;    // a source used twice is staged once
+            {
+                gather_features(X, RS, p.slot[ph][i], p.src[set][ph][i], p.src_c[ph][i], RS, [&](int r) -> long long {
+                    return (r < rt && r0 + r < rows) ? r0 + r : -1;
+                });
+            }
+        }
+    compute_sync();
+    const int m = pipe.my_row();
+    const bool row_ok = m < rt && r0 + m < rows;
+    for (int ph = 0; ph < p.nphase; ++ph) {
+        // global sources of this phase -> their place in the concatenation
+        int off = 0, prev_off_next = 0;
+        for (int i = 0; i < p.nsrc[ph]; ++i) {
+            if (!p.src_prev[ph][i]) pipe.load_a_from_smem(X, p.slot[ph][i], p.src_c[ph][i], off);
+            off += p.src_c[ph][i];
+        }
+        if (ph + 1 < p.nphase) {
+            int o = 0;
+            for (int i = 0; i < p.nsrc[ph + 1]; ++i) { if (p.src_prev[ph + 1][i]) prev_off_next = o; o += p.src_c[ph + 1][i]; }
+        }
+        pipe.signal_a_ready();
+        for (int l = 0; l < p.nl[ph]; ++l) {
+            const bool last_layer = l == p.nl[ph] - 1;
+            const bool last_phase = ph == p.nphase - 1;
+            const int n = p.cout[ph][l];
+            float* gout = !last_layer ? nullptr : (last_phase ? p.out[set] : p.out_phase0[set]);
+            pipe.epilogue<true>(n, [&](int b, const float (&v)[16]) {
+                if (!last_layer) pipe.store_a(0, b, v);
+                else if (!last_phase) pipe.store_a(prev_off_next, b, v);
+                if (gout != nullptr && row_ok) {
+                    float4* dst = reinterpret_cast<float4*>(gout + (r0 + m) * n + b * 16);
+                    dst[0] = make_float4(v[0], v[1], v[2], v[3]);
+                    dst[1] = make_float4(v[4], v[5], v[6], v[7]);
+                    dst[2] = make_float4(v[8], v[9], v[10], v[11]);
+                    dst[3] = make_float4(v[12], v[13], v[14], v[15]);
+                }
+            });
+            if (!last_layer) pipe.signal_a_ready();
+            // after the last layer of a non-final phase the next iteration loads the other sources and signals
+        }
+    }
+    pipe.finish();
 }
 
 // ================================================================================================
@@ -562,9 +934,63 @@ static int check_queries(const elo_queries* q, const char* who)
 
 static int width_ok(int c) { return c == 64 || c == 128; }
 
+// MLP engine: 1 = tcgen05 tensor cores (3xTF32, 128-row tiles), 0 = fp32 FFMA (64/128-row tiles)
+static int g_engine = 1;
+
+struct TcChoice { int per_tile, tiles; };
+
+// 128-row tiles: `units` work items of `rows_per_unit` rows, spread evenly over the waves they need
+static TcChoice choose_tc_tile(long long units, int rows_per_unit, int nsets)
+{
+    const int sms = device_info().sm_count;
+    const int cap = TC_ROWS / rows_per_unit;
+    long long tiles = (units + cap - 1) / cap;
+    const long long waves = (tiles * nsets + sms - 1) / sms;
+    long long slots = waves * sms / nsets;
+    if (slots < tiles) slots = tiles;
+    if (slots > units) slots = units;
+    int per = (int)((units + slots - 1) / slots);
+    if (per > cap) per = cap;
+    return TcChoice{per, (int)((units + per - 1) / per)};
+}
+
+// shared memory of a tensor-core tile besides the weight ring
+static size_t tc_base_smem(int kt, size_t staging_floats)
+{
+    return align16((2 * MAX_RING + 2) * 8) + 16 + align16((size_t)kt * 8) + align16(TC_ROWS * 4) +
+           align16(TC_ROWS * 16) + align16(staging_floats * 4);
+}
+
+static int tc_pick_ring(size_t base, int total_chunks)
+{
+    long long n = ((long long)SMEM_LIMIT - (long long)base) / TC_CHUNK_BYTES;
+    if (n > MAX_RING) n = MAX_RING;
+    if (n > total_chunks) n = total_chunks;
+    return (int)n;
+}
+
+template <typename Kernel, typename Params>
+static int launch_tc(Kernel kern, const Params& p, dim3 grid, size_t bytes, cudaStream_t st, const char* what)
+{
+    int rc = set_smem(kern, bytes, what);
+    if (rc) return rc;
+    kern<<<grid, TC_LAUNCH_THREADS, bytes, st>>>(p);
+    count_launches(1);
+    cudaError_t err = cudaGetLastError();
+    return err == cudaSuccess ? ELO_OK : set_cuda_error(err, what);
+}
+
 }  // namespace elo
 
 using namespace elo;
+
+extern "C" int elo_set_mlp_engine(int engine)
+{
+    if (engine != 0 && engine != 1) return set_error(ELO_ERR_INVALID_ARGUMENT, "mlp engine: 0 = fp32 FFMA, 1 = tcgen05 3xTF32");
+    g_engine = engine;
+    return ELO_OK;
+}
+extern "C" int elo_get_mlp_engine(void) { return g_engine; }
 
 extern "C" int elo_group_mlp_max(const elo_group_mlp_desc* d, void* stream)
 {
@@ -605,6 +1031,20 @@ extern "C" int elo_group_mlp_max(const elo_group_mlp_desc* d, void* stream)
         p.q_end[s] = p.q_base[s] + per_set;
     }
     const int kt = p.g.kt, xch = (3 + p.Cf + 3) & ~3;
+    if (g_engine == 1) {
+        if (p.g.K > TC_ROWS) return set_error(ELO_ERR_UNSUPPORTED, "group_mlp_max: K > 128");
+        int cin_t = 3 + p.Cf, chunks_t = 0;
+        for (int l = 0; l < p.nl; ++l) { chunks_t += tc_layer_chunks(cin_t, p.cout[l]); cin_t = p.cout[l]; }
+        p.total_chunks = chunks_t;
+        const int stage_ch = xch > p.cout[p.nl - 1] ? xch : p.cout[p.nl - 1];
+        const size_t base = tc_base_smem(kt, (size_t)stage_ch * TC_ROWS);
+        p.nring = tc_pick_ring(base, chunks_t);
+        if (p.nring < 2) return set_error(ELO_ERR_UNSUPPORTED, "group_mlp_max: tile does not fit shared memory");
+        const TcChoice tc = choose_tc_tile(per_set, p.g.K, d->nsets);
+        p.qt = tc.per_tile;
+        return launch_tc(group_mlp_max_tc_kernel, p, dim3(tc.tiles, d->nsets), base + (size_t)p.nring * TC_CHUNK_BYTES,
+                         (cudaStream_t)stream, "group_mlp_max (tensor core) launch");
+    }
     auto smem = [&](int nb) { return common_smem(kt, 64 * nb) + (size_t)(xch + 256) * 64 * nb * 4; };
     const TileChoice tc = choose_tile(per_set, p.g.K, d->nsets, smem);
     if (tc.nb == 0) return set_error(ELO_ERR_UNSUPPORTED, "group_mlp_max: tile does not fit shared memory");
@@ -647,6 +1087,20 @@ extern "C" int elo_cost_volume_1(const elo_cost_volume_desc* d, void* stream)
     p.xyz1 = d->xyz1; p.xyz2 = d->xyz2; p.f1 = d->f1; p.f2 = d->f2; p.random_hw = d->window_q.random_hw;
     p.weights = d->weights_1; p.out = d->stage1_out; p.dbg_nbr = d->dbg_nbr_q; p.nbr_in = d->nbr_q;
     const int kt = p.g.kt, xch = (xc + 3) & ~3;
+    if (g_engine == 1) {
+        if (!p.nbr_in) return set_error(ELO_ERR_INVALID_ARGUMENT, "cost_volume_1: the tensor-core engine takes nbr_q from elo_multi_search");
+        p.total_chunks = tc_layer_chunks(xc, 128) + tc_layer_chunks(128, 64) + tc_layer_chunks(64, 64) +
+                         tc_layer_chunks(10, 64) + tc_layer_chunks(128, 128) + tc_layer_chunks(128, 64);
+        const int stage_ch = xch > 128 ? xch : 128;
+        const size_t base = tc_base_smem(0, (size_t)stage_ch * TC_ROWS);
+        p.nring = tc_pick_ring(base, p.total_chunks);
+        if (p.nring < 2) return set_error(ELO_ERR_UNSUPPORTED, "cost_volume_1: tile does not fit shared memory");
+        const TcChoice tc = choose_tc_tile(p.total_q, p.g.K, 1);
+        p.qt = tc.per_tile;
+        p.g.kt = 0;
+        return launch_tc(cost_volume_1_tc_kernel, p, dim3(tc.tiles), base + (size_t)p.nring * TC_CHUNK_BYTES,
+                         (cudaStream_t)stream, "cost_volume_1 (tensor core) launch");
+    }
     auto smem = [&](int nb) {
         // the select-K scratch (8 warps x kt x 8 B) must fit in the A|Bf|Cb region it aliases
         if ((size_t)kt * 64 > (size_t)320 * 64 * nb * 4) return (size_t)1 << 30;
@@ -690,6 +1144,18 @@ extern "C" int elo_cost_volume_2(const elo_cost_volume_desc* d, void* stream)
     p.xyz1 = d->xyz1; p.f1 = d->f1; p.cv1 = d->stage1_out; p.random_hw = d->window_p.random_hw;
     p.weights = d->weights_2; p.out = d->out; p.dbg_nbr = d->dbg_nbr_p; p.nbr_in = d->nbr_p;
     const int kt = p.g.kt;
+    if (g_engine == 1) {
+        if (!p.nbr_in) return set_error(ELO_ERR_INVALID_ARGUMENT, "cost_volume_2: the tensor-core engine takes nbr_p from elo_multi_search");
+        p.total_chunks = tc_layer_chunks(10, 64) + tc_layer_chunks(128 + d->C, 128) + tc_layer_chunks(128, 64);
+        const size_t base = tc_base_smem(0, (size_t)(144 + d->C) * TC_ROWS);
+        p.nring = tc_pick_ring(base, p.total_chunks);
+        if (p.nring < 2) return set_error(ELO_ERR_UNSUPPORTED, "cost_volume_2: tile does not fit shared memory");
+        const TcChoice tc = choose_tc_tile(p.total_q, p.g.K, 1);
+        p.qt = tc.per_tile;
+        p.g.kt = 0;
+        return launch_tc(cost_volume_2_tc_kernel, p, dim3(tc.tiles), base + (size_t)p.nring * TC_CHUNK_BYTES,
+                         (cudaStream_t)stream, "cost_volume_2 (tensor core) launch");
+    }
     auto smem = [&](int nb) { return common_smem(kt, 64 * nb) + (size_t)(12 + 128 + d->C + 192) * 64 * nb * 4; };
     const TileChoice tc = choose_tile(p.total_q, p.g.K, 1, smem);
     if (tc.nb == 0) return set_error(ELO_ERR_UNSUPPORTED, "cost_volume_2: tile does not fit shared memory");
@@ -758,6 +1224,35 @@ extern "C" int elo_row_mlp(const elo_row_mlp_desc* d, void* stream)
             }
     }
     const int xch = (xmax + 3) & ~3;
+    if (g_engine == 1) {
+        // staging slots: every distinct global source once (same pattern required for both sets)
+        int stage_ch = 0, chunks_t = 0;
+        for (int ph = 0; ph < p.nphase; ++ph) {
+            int cin_t = 0;
+            for (int i = 0; i < p.nsrc[ph]; ++i) {
+                p.slot[ph][i] = -1; p.stage_here[ph][i] = 0;
+                cin_t += p.src_c[ph][i];
+                if (p.src_c[ph][i] & 15) return set_error(ELO_ERR_UNSUPPORTED, "row_mlp: tensor-core engine needs channels % 16 == 0");
+                if (p.src_prev[ph][i]) continue;
+                for (int ph2 = 0; ph2 <= ph && p.slot[ph][i] < 0; ++ph2)
+                    for (int j = 0; j < (ph2 == ph ? i : p.nsrc[ph2]); ++j)
+                        if (!p.src_prev[ph2][j] && p.src[0][ph2][j] == p.src[0][ph][i] && p.src[1][ph2][j] == p.src[1][ph][i] &&
+                            p.src_c[ph2][j] == p.src_c[ph][i]) { p.slot[ph][i] = p.slot[ph2][j]; break; }
+                if (p.slot[ph][i] < 0) { p.slot[ph][i] = stage_ch; p.stage_here[ph][i] = 1; stage_ch += p.src_c[ph][i]; }
+            }
+            if (cin_t > 192) return set_error(ELO_ERR_UNSUPPORTED, "row_mlp: more than 192 input channels");
+            for (int l = 0; l < p.nl[ph]; ++l) { chunks_t += tc_layer_chunks(cin_t, p.cout[ph][l]); cin_t = p.cout[ph][l]; }
+        }
+        p.total_chunks = chunks_t;
+        p.stage_ch = stage_ch;
+        const size_t base = tc_base_smem(0, (size_t)stage_ch * TC_ROWS);
+        p.nring = tc_pick_ring(base, chunks_t);
+        if (p.nring < 2) return set_error(ELO_ERR_UNSUPPORTED, "row_mlp: tile does not fit shared memory");
+        const TcChoice tc = choose_tc_tile(p.rows, 1, d->nsets);
+        p.rt = tc.per_tile;
+        return launch_tc(row_mlp_tc_kernel, p, dim3(tc.tiles, d->nsets), base + (size_t)p.nring * TC_CHUNK_BYTES,
+                         (cudaStream_t)stream, "row_mlp (tensor core) launch");
+    }
     auto smem = [&](int nb) { return align16(2 * MAX_RING * 8) + (size_t)(xch + 256) * 64 * nb * 4; };
     const TileChoice tc = choose_tile(p.rows, 1, d->nsets, smem);
     if (tc.nb == 0) return set_error(ELO_ERR_UNSUPPORTED, "row_mlp: tile does not fit shared memory");

@@ -25,6 +25,36 @@ def pack_stream(P, scopes):
     return torch.cat(parts).contiguous()
 
 
+def split_tf32(w):
+    """w = hi + lo with hi = w truncated to tf32 (low 13 mantissa bits cleared), lo = w - hi (exact in fp32)."""
+    w = w.float().contiguous()
+    hi = (w.view(torch.int32) & -8192).view(torch.float32)
+    return hi, (w - hi)
+
+
+def pack_stream_tc(P, scopes):
+    """Stream for the tensor-core engine (csrc/elo_tc_engine.cuh): per layer ceil(Cin / R) chunks of
+    R = 2048 / Cout k-rows; a chunk is [hi | lo], each half in the canonical K-major core-matrix order
+    [R/4][Cout][4] (k-rows beyond Cin are zero); after all chunks, the folded biases of all layers."""
+    chunks, biases = [], []
+    for scope in scopes:
+        w, b = fold_bn(P, scope)
+        cin, cout = w.shape
+        if cout not in (64, 128):
+            raise ValueError("%s: the GEMM engine takes 64- or 128-wide layers, got %d" % (scope, cout))
+        R = CHUNK_FLOATS // cout
+        nch = (cin + R - 1) // R
+        padded = torch.zeros(nch * R, cout, dtype=torch.float32)
+        padded[:cin] = w.float()
+        hi, lo = split_tf32(padded)
+        for c in range(nch):
+            for part in (hi, lo):
+                blk = part[c * R:(c + 1) * R].reshape(R // 4, 4, cout).permute(0, 2, 1).contiguous()
+                chunks.append(blk.reshape(-1))
+        biases.append(b.float().reshape(-1))
+    return torch.cat(chunks + biases).contiguous()
+
+
 def pack_plain(P, scopes):
     """Plain packing for the register-MLP set-conv: W1, b1, W2, b2, W3, b3 (row-major [Cin][Cout])."""
     parts = []

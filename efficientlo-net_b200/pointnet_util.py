@@ -323,6 +323,12 @@ def cost_volume(warped_xyz1_proj, xyz2_proj, points1_proj, points2_proj, kernel_
         raise ValueError("%s/CV_0 expects %d input channels, got 10 + 2*%d" % (scope, store.cin(sc("CV_0")), C))
     perm_q = _perm(random_hw_q, kernel_size2[0] * kernel_size2[1], dev)
     perm_p = _perm(random_hw_p, kernel_size1[0] * kernel_size1[1], dev)
+    if nbr_q is None or nbr_p is None:
+        # stand-alone call: both neighbour searches in one launch (pwclo_model batches them per level itself)
+        allq = (H, W, 1, 1)
+        nbr_q, nbr_p = multi_search([
+            search_spec(True, xyz1, xyz2, allq, kernel_size2, nsample_q, 1000.0, 1, 1, perm_q),
+            search_spec(False, xyz1, xyz1, allq, kernel_size1, nsample, distance, 1, 1, perm_p)])
     stage1 = torch.empty((B, H * W, 64), dtype=torch.float32, device=dev)
     out = torch.empty((B, H * W, 64), dtype=torch.float32, device=dev)
     dq = torch.full((B, H * W, nsample_q), -2, dtype=torch.int32, device=dev) if debug is not None else None

@@ -23,9 +23,13 @@ class ParamStore:
         self._cache = {}
 
     def stream(self, scopes):
-        key = ("stream",) + tuple(scopes)
+        """Packed weights of a layer chain in the format of the MLP engine currently selected."""
+        from . import _lib
+        tc = _lib.mlp_engine() == 1
+        key = ("stream_tc" if tc else "stream",) + tuple(scopes)
         if key not in self._cache:
-            self._cache[key] = packing.pack_stream(self.P, scopes).to(self.device)
+            pack = packing.pack_stream_tc if tc else packing.pack_stream
+            self._cache[key] = pack(self.P, scopes).to(self.device)
         return self._cache[key]
 
     def plain(self, scopes):

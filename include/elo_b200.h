@@ -64,10 +64,19 @@ int elo_fused_conv_random_k(int batch_size, int H, int W, int npoints, int kerne
  * reduce_max / softmax / reduce_sum).  Descriptors are plain C structs; tensors are fp32,
  * C-contiguous, channel-last, on the device.
  *
- * Weights are the packed stream efficientlo-net_b200/packing.py produces: per layer, rows 0..Cin-1 =
- * W'[k][0..Cout) and row Cin = bias, both with the inference batch-norm folded in, then zero rows up to
- * a multiple of (2048 / Cout); layers back to back in execution order.
+ * Weights are packed by efficientlo-net_b200/packing.py with the inference batch-norm folded in.
+ * FFMA engine: per layer, rows 0..Cin-1 = W'[k][0..Cout), row Cin = bias, zero rows up to a multiple of
+ * (2048 / Cout); layers back to back in execution order.  Tensor-core engine: per layer ceil(Cin / R)
+ * chunks of R = 2048 / Cout k-rows, each chunk [hi | lo] tf32 halves in the K-major core-matrix order
+ * [R/4][Cout][4]; after the last chunk of the last layer, the biases of all layers in order.
  */
+/* Which engine runs the per-group MLPs of the fused blocks below:
+ *   1 (default)  tcgen05 tensor cores, tf32 x 3 split (fp32-grade accuracy), 128-row tiles, activations in TMEM;
+ *   0            fp32 FFMA out of shared memory (the first implementation; kept as a cross-check).
+ * The packed `weights` a descriptor carries must match the engine (packing.pack_stream_tc / pack_stream). */
+int elo_set_mlp_engine(int engine);
+int elo_get_mlp_engine(void);
+
 typedef struct {
     int kernel_size_H, kernel_size_W, K;
     float distance;
@@ -214,6 +223,11 @@ typedef struct {
     float *q_out, *t_out, *q_norm_out, *pooled_out;
 } elo_pose_head_desc;
 int elo_pose_head(const elo_pose_head_desc *desc, void *stream);
+
+/* Test hook for the tensor-core dense layer (tcgen05, 3xTF32): Y[128 x N] = act(X[128 x K] W[K x N] + bias),
+ * X, W, Y row-major on the device, K % 16 == 0, K <= 192, N in {64, 128}. */
+int elo_tc_dense_test(const float *X, const float *W, const float *bias, float *Y, int K, int N, int relu,
+                      void *stream);
 
 /* Strided xyz pyramid (pwclo_model.py:88-114, get_selected_idx + gather_nd): level l of 4 keeps pixel
  * (i*stride_h[l], j*stride_w[l]) of xyz_in (samples,H,W,3) for i < out_h[l], j < out_w[l]; strides are

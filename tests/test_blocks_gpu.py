@@ -14,6 +14,14 @@ RTOL, ATOL = 1e-4, 1e-5
 H_IN, W_IN, NPTS = 64, 1800, 150000
 
 
+@pytest.fixture(params=[1, 0], ids=["tcgen05", "ffma"], autouse=True)
+def mlp_engine(request, elo):
+    """Every block test runs on both MLP engines: tensor cores (3xTF32, the default) and fp32 FFMA."""
+    elo._lib.set_mlp_engine(request.param)
+    yield request.param
+    elo._lib.set_mlp_engine(1)
+
+
 def close(got, want, what, rtol=RTOL, atol=ATOL):
     got, want = got.detach().cpu().double(), want.detach().cpu().double()
     assert got.shape == want.shape, "%s: shape %s vs %s" % (what, tuple(got.shape), tuple(want.shape))
