@@ -63,6 +63,19 @@ __device__ __forceinline__ void mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_
         "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"((uint32_t)accumulate)
         : "memory");
 }
+// same with a compile-time accumulate flag: no predicate arithmetic in the issue loop
+template <bool ACC>
+__device__ __forceinline__ void mma_ts_c(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc)
+{
+    if (ACC)
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.eq.u32 p, 1, 1;\n\t"
+                     "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem), "r"(a_tmem),
+                     "l"(b_desc), "r"(idesc) : "memory");
+    else
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.eq.u32 p, 1, 0;\n\t"
+                     "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem), "r"(a_tmem),
+                     "l"(b_desc), "r"(idesc) : "memory");
+}
 // arrive on an mbarrier once every MMA issued so far by this thread has completed
 __device__ __forceinline__ void mma_commit(uint64_t* bar)
 {

@@ -40,14 +40,29 @@ struct TcPipe {
     uint32_t tbase;       // TMEM base address
     uint32_t layer;       // layers completed so far (parity of a_ready / done)
     uint32_t chunk;       // chunks consumed so far (MMA warp)
-    const float* bias;    // biases of the remaining layers (compute warps advance it)
+    const float* bias;    // biases of the remaining layers, in shared memory (compute warps advance it)
+    long long* tlog;      // optional phase timestamps (ns) of CTA (0,0): compute thread 0 -> [0,32), MMA thread -> [32,64)
+
+    __device__ __forceinline__ void stamp(int id)
+    {
+        if (tlog != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && (threadIdx.x & 31) == 0 &&
+            ((threadIdx.x >> 5) == 0 || (threadIdx.x >> 5) == COMPUTE_WARPS + 1)) {
+            long long t;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+            tlog[id + ((threadIdx.x >> 5) == 0 ? 0 : 32)] = t;
+        }
+    }
 
     // all threads; bars must hold 2 * MAX_RING + 2 mbarriers; contains __syncthreads
     __device__ __forceinline__ void init(float* ring_, uint64_t* bars, uint32_t nring_, uint32_t* tmem_holder,
-                                         const float* bias_)
+                                         const float* bias_gmem, float* bias_smem, int nbias, long long* tlog_ = nullptr)
     {
+        tlog = tlog_;
+        stamp(0);
         ring = ring_; full = bars; empty = bars + MAX_RING; a_ready = bars + 2 * MAX_RING; done = a_ready + 1;
-        nring = nring_; layer = 0; chunk = 0; bias = bias_;
+        nring = nring_; layer = 0; chunk = 0; bias = bias_smem;
+        // every epilogue needs its biases at once: one L2 round trip here instead of one per layer
+        for (int i = threadIdx.x; i < nbias; i += blockDim.x) bias_smem[i] = __ldg(bias_gmem + i);
         if (threadIdx.x == 0) {
             for (uint32_t i = 0; i < nring; ++i) { mbar_init(full + i, 1); mbar_init(empty + i, 1); }
             mbar_init(a_ready, COMPUTE_WARPS);
@@ -59,6 +74,7 @@ struct TcPipe {
         __syncthreads();
         tc::fence_after_sync();
         tbase = *tmem_holder;
+        stamp(1);
     }
     // after the last epilogue: compute warps only
     __device__ __forceinline__ void finish()
@@ -81,36 +97,52 @@ struct TcPipe {
     }
 
     // ---- MMA warp (lane 0) ------------------------------------------------------------------------
-    // D[128 x n] = A[:, a_col : a_col + cin] * W  with the 3xTF32 split
-    __device__ __forceinline__ void issue_layer(uint32_t a_col, uint32_t cin, uint32_t n)
+    // D[128 x N] = A[:, a_col : a_col + cin] * W  with the 3xTF32 split.  The issuing thread is the
+    // serial bottleneck of a small-N layer (a 128 x 64 x 8 MMA occupies the tensor pipe for ~35 cycles),
+    // so the loop is kept to a few instructions per MMA: descriptors are advanced by adds, N is a
+    // compile-time constant and the accumulate flags are immediates.
+    template <uint32_t N>
+    __device__ __forceinline__ void issue_layer_n(uint32_t a_col, uint32_t cin)
     {
+        constexpr uint32_t R = 2048u / N;              // k-rows per chunk
+        constexpr uint32_t KSPC = R / 8u;              // K=8 steps per chunk
+        constexpr uint32_t KSTEP16 = 2u * N;           // 16-byte units between consecutive K-steps of B
         mbar_wait(a_ready, layer & 1u);
         tc::fence_after_sync();
-        const uint32_t R = 2048u / n;                  // k-rows per chunk
-        const uint32_t nks = (cin + 7u) >> 3;          // K = 8 per MMA
-        const uint32_t nchunks = (cin + R - 1u) / R;
-        const uint32_t idesc = tc::idesc_tf32(n);
-        const uint32_t lbo = n * 16u, sbo = 128u;
+        stamp(2 + 2 * (int)layer);
+        const uint32_t nks = (cin + 7u) >> 3;
+        const uint32_t idesc = tc::idesc_tf32(N);
+        const uint64_t desc0 = tc::smem_desc(tc::smem_addr(ring), N * 16u, 128u);
+        const uint32_t d = tbase + TC_D_COL;
+        uint32_t a_hi = tbase + a_col;
         uint32_t ks = 0;
-        for (uint32_t c = 0; c < nchunks; ++c) {
+        while (ks < nks) {
             const uint32_t slot = chunk % nring;
             mbar_wait(full + slot, (chunk / nring) & 1u);
             tc::fence_after_sync();
-            const float* hi = ring + (size_t)slot * TC_CHUNK_FLOATS;
-            const float* lo = hi + TC_CHUNK_FLOATS / 2;
-            for (uint32_t j = 0; j < R / 8u && ks < nks; ++j, ++ks) {
-                const uint64_t bhi = tc::smem_desc(tc::smem_addr(hi + (size_t)j * 2u * n * 4u), lbo, sbo);
-                const uint64_t blo = tc::smem_desc(tc::smem_addr(lo + (size_t)j * 2u * n * 4u), lbo, sbo);
-                const uint32_t a_hi = tbase + a_col + ks * 8u, a_lo = a_hi + TC_A_LO;
-                tc::mma_ts(tbase + TC_D_COL, a_hi, bhi, idesc, ks > 0);
-                tc::mma_ts(tbase + TC_D_COL, a_lo, bhi, idesc, true);
-                tc::mma_ts(tbase + TC_D_COL, a_hi, blo, idesc, true);
+            uint64_t bhi = desc0 + (uint64_t)slot * (TC_CHUNK_BYTES >> 4);
+            uint64_t blo = bhi + (TC_CHUNK_BYTES >> 5);
+#pragma unroll
+            for (uint32_t j = 0; j < KSPC; ++j) {
+                if (ks < nks) {
+                    if (ks == 0) tc::mma_ts_c<false>(d, a_hi, bhi, idesc);
+                    else tc::mma_ts_c<true>(d, a_hi, bhi, idesc);
+                    tc::mma_ts_c<true>(d, a_hi + TC_A_LO, bhi, idesc);
+                    tc::mma_ts_c<true>(d, a_hi, blo, idesc);
+                    a_hi += 8u; bhi += KSTEP16; blo += KSTEP16; ++ks;
+                }
             }
             tc::mma_commit(empty + slot);              // slot reusable once these MMAs have read it
             ++chunk;
         }
         tc::mma_commit(done);
+        stamp(3 + 2 * (int)layer);
         ++layer;
+    }
+    __device__ __forceinline__ void issue_layer(uint32_t a_col, uint32_t cin, uint32_t n)
+    {
+        if (n == 128u) issue_layer_n<128u>(a_col, cin);
+        else issue_layer_n<64u>(a_col, cin);
     }
 
     // ---- compute warps ------------------------------------------------------------------------------
@@ -167,18 +199,24 @@ struct TcPipe {
     {
         mbar_wait(done, layer & 1u);
         tc::fence_after_sync();
+        stamp(8 + 2 * (int)layer);
         const uint32_t addr = my_lane_addr() + TC_D_COL;
         for (int b = my_half(); b * 16 < n; b += 2) {
             float v[16];
             tc::tmem_ld16(addr + b * 16, v);
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-                v[i] += __ldg(bias + b * 16 + i);
-                if (RELU) v[i] = fmaxf(v[i], 0.f);
+            for (int i = 0; i < 16; i += 4) {
+                const float4 bv = *reinterpret_cast<const float4*>(bias + b * 16 + i);
+                v[i] += bv.x; v[i + 1] += bv.y; v[i + 2] += bv.z; v[i + 3] += bv.w;
+            }
+            if (RELU) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
             }
             sink(b, v);
         }
         bias += n;
+        stamp(9 + 2 * (int)layer);
         ++layer;
     }
     // sink helpers

@@ -39,6 +39,7 @@ struct GroupMlpParams {
     float* out[2];
     int* dbg_nbr[2];
     const int* nbr_in[2];
+    long long* tlog;
 };
 
 template <int NB>
@@ -149,6 +150,7 @@ struct Cv1Params {
     float* out;
     int* dbg_nbr;
     const int* nbr_in;
+    long long* tlog;
 };
 
 // xyz part of a cost-volume row: [p, q, q - p, sqrt(|q - p|^2 + 1e-20)] (utils/pointnet_util.py:60-63)
@@ -283,6 +285,7 @@ struct Cv2Params {
     float* out;
     int* dbg_nbr;
     const int* nbr_in;
+    long long* tlog;
 };
 
 template <int NB>
@@ -395,6 +398,7 @@ struct RowMlpParams {
     const float* weights[2];
     float* out[2];
     float* out_phase0[2];      // optional: also store phase 0's result (rows, cout) -- may be null
+    long long* tlog;
 };
 
 template <int NB>
@@ -475,8 +479,10 @@ __global__ void __launch_bounds__(LAUNCH_THREADS, 1) row_mlp_kernel(const RowMlp
 // streamed by the TMA warp, MMAs issued by a dedicated warp.  Tiles have TC_ROWS = 128 rows.
 // `weights` here = [TC stream: total_chunks x 4096 floats][biases of all layers, in order].
 
+constexpr int TC_MAX_BIAS = 768;     // channels summed over the layers of one kernel (cost volume stage 1: 512)
+
 struct TcSmem {
-    float* ring; uint64_t* bars; uint32_t* tmem_holder; int2* off; int* nbr; float* ctr; float* X;
+    float* ring; uint64_t* bars; uint32_t* tmem_holder; float* bias; int2* off; int* nbr; float* ctr; float* X;
 };
 
 __device__ __forceinline__ TcSmem tc_carve(unsigned char* raw, int nring, int kt, size_t staging_floats)
@@ -486,6 +492,7 @@ __device__ __forceinline__ TcSmem tc_carve(unsigned char* raw, int nring, int kt
     m.ring = sc.take<float>((size_t)nring * TC_CHUNK_FLOATS);
     m.bars = sc.take<uint64_t>(2 * MAX_RING + 2);
     m.tmem_holder = sc.take<uint32_t>(4);
+    m.bias = sc.take<float>(TC_MAX_BIAS);
     m.off = sc.take<int2>(kt);
     m.nbr = sc.take<int>(TC_ROWS);
     m.ctr = sc.take<float>(TC_ROWS * 4);
@@ -504,7 +511,10 @@ __global__ void __launch_bounds__(TC_LAUNCH_THREADS, 1) group_mlp_max_tc_kernel(
     const int set = blockIdx.y, warp = threadIdx.x >> 5;
     const Window g = p.g;
     TcPipe pipe;
-    pipe.init(sm.ring, sm.bars, p.nring, sm.tmem_holder, p.weights[set] + (size_t)p.total_chunks * TC_CHUNK_FLOATS);
+    int nbias = 0;
+    for (int l = 0; l < p.nl; ++l) nbias += p.cout[l];
+    pipe.init(sm.ring, sm.bars, p.nring, sm.tmem_holder, p.weights[set] + (size_t)p.total_chunks * TC_CHUNK_FLOATS,
+              sm.bias, nbias, p.tlog);
     if (warp == COMPUTE_WARPS) { pipe.produce(p.weights[set], p.total_chunks); return; }
     if (warp == COMPUTE_WARPS + 1) {
         if ((threadIdx.x & 31) == 0) {
@@ -586,7 +596,8 @@ __global__ void __launch_bounds__(TC_LAUNCH_THREADS, 1) cost_volume_1_tc_kernel(
     const int warp = threadIdx.x >> 5;
     const Window g = p.g;
     TcPipe pipe;
-    pipe.init(sm.ring, sm.bars, p.nring, sm.tmem_holder, p.weights + (size_t)p.total_chunks * TC_CHUNK_FLOATS);
+    pipe.init(sm.ring, sm.bars, p.nring, sm.tmem_holder, p.weights + (size_t)p.total_chunks * TC_CHUNK_FLOATS,
+              sm.bias, 128 + 64 + 64 + 64 + 128 + 64, p.tlog);
     if (warp == COMPUTE_WARPS) { pipe.produce(p.weights, p.total_chunks); return; }
     if (warp == COMPUTE_WARPS + 1) {
         if ((threadIdx.x & 31) == 0) {
@@ -607,6 +618,7 @@ __global__ void __launch_bounds__(TC_LAUNCH_THREADS, 1) cost_volume_1_tc_kernel(
     // this kernel takes its neighbour table from elo_multi_search (the launcher guarantees nbr_in)
     tile_load_nbr(p.qs, g.K, p.xyz1, p.nbr_in, q0, p.qt, p.total_q, nbr, ctr);
     compute_sync();
+    pipe.stamp(2);
     for (int r = threadIdx.x; r < RS; r += CTA_THREADS) {
         const int q = r / g.K;
         float px = 0.f, py = 0.f, pz = 0.f, qx = 0.f, qy = 0.f, qz = 0.f;
@@ -637,6 +649,7 @@ __global__ void __launch_bounds__(TC_LAUNCH_THREADS, 1) cost_volume_1_tc_kernel(
         });
     }
     compute_sync();
+    pipe.stamp(3);
     // the 10 xyz channels are needed again by CV_xyz after the tile's A region has been overwritten
     float x10[16];
     {
@@ -646,6 +659,7 @@ __global__ void __launch_bounds__(TC_LAUNCH_THREADS, 1) cost_volume_1_tc_kernel(
     }
     pipe.load_a_from_smem(X, 0, xc, 0);
     pipe.signal_a_ready();
+    pipe.stamp(4);
     float* S = X;                               // staging reused: F at channels [0,64), logits at [64,128)
     pipe.epilogue<true>(128, [&](int b, const float (&v)[16]) { pipe.store_a(0, b, v); });        // CV_0
     pipe.signal_a_ready();
@@ -669,16 +683,19 @@ __global__ void __launch_bounds__(TC_LAUNCH_THREADS, 1) cost_volume_1_tc_kernel(
     pipe.signal_a_ready();
     pipe.epilogue<true>(64, [&](int b, const float (&v)[16]) { pipe.store_smem(S, 64, b, v); });  // logits
     compute_sync();
+    pipe.stamp(5);
     for (int t = threadIdx.x; t < p.qt * 64; t += CTA_THREADS) {
         const int q = t >> 6, c = t & 63;
         const long long gq = q0 + q;
         if (gq >= p.total_q) break;
         p.out[gq * 64 + c] = softmax_pool(S + 64 * RS, S, nbr + q * g.K, c, q * g.K, g.K, RS);
     }
+    pipe.stamp(6);
     if (p.dbg_nbr != nullptr)
         for (int t = threadIdx.x; t < p.qt * g.K; t += CTA_THREADS)
             if (q0 + t / g.K < p.total_q) p.dbg_nbr[q0 * g.K + t] = nbr[t];
     pipe.finish();
+    pipe.stamp(7);
 }
 
 __global__ void __launch_bounds__(TC_LAUNCH_THREADS, 1) cost_volume_2_tc_kernel(const Cv2Params p)
@@ -691,7 +708,8 @@ __global__ void __launch_bounds__(TC_LAUNCH_THREADS, 1) cost_volume_2_tc_kernel(
     const int warp = threadIdx.x >> 5;
     const Window g = p.g;
     TcPipe pipe;
-    pipe.init(sm.ring, sm.bars, p.nring, sm.tmem_holder, p.weights + (size_t)p.total_chunks * TC_CHUNK_FLOATS);
+    pipe.init(sm.ring, sm.bars, p.nring, sm.tmem_holder, p.weights + (size_t)p.total_chunks * TC_CHUNK_FLOATS,
+              sm.bias, 64 + 128 + 64, p.tlog);
     if (warp == COMPUTE_WARPS) { pipe.produce(p.weights, p.total_chunks); return; }
     if (warp == COMPUTE_WARPS + 1) {
         if ((threadIdx.x & 31) == 0) {
@@ -777,7 +795,11 @@ __global__ void __launch_bounds__(TC_LAUNCH_THREADS, 1) row_mlp_tc_kernel(const 
     const int set = blockIdx.y, warp = threadIdx.x >> 5;
     TcSmem sm = tc_carve(smem_raw, p.nring, 0, (size_t)p.stage_ch * RS);
     TcPipe pipe;
-    pipe.init(sm.ring, sm.bars, p.nring, sm.tmem_holder, p.weights[set] + (size_t)p.total_chunks * TC_CHUNK_FLOATS);
+    int nbias = 0;
+    for (int ph = 0; ph < p.nphase; ++ph)
+        for (int l = 0; l < p.nl[ph]; ++l) nbias += p.cout[ph][l];
+    pipe.init(sm.ring, sm.bars, p.nring, sm.tmem_holder, p.weights[set] + (size_t)p.total_chunks * TC_CHUNK_FLOATS,
+              sm.bias, nbias, p.tlog);
     if (warp == COMPUTE_WARPS) { pipe.produce(p.weights[set], p.total_chunks); return; }
     if (warp == COMPUTE_WARPS + 1) {
         if ((threadIdx.x & 31) == 0)
@@ -934,6 +956,8 @@ static int check_queries(const elo_queries* q, const char* who)
 
 static int width_ok(int c) { return c == 64 || c == 128; }
 
+static long long* g_tlog = nullptr;    // optional device buffer of 64 timestamps (elo_set_time_log)
+
 // MLP engine: 1 = tcgen05 tensor cores (3xTF32, 128-row tiles), 0 = fp32 FFMA (64/128-row tiles)
 static int g_engine = 1;
 
@@ -957,8 +981,8 @@ static TcChoice choose_tc_tile(long long units, int rows_per_unit, int nsets)
 // shared memory of a tensor-core tile besides the weight ring
 static size_t tc_base_smem(int kt, size_t staging_floats)
 {
-    return align16((2 * MAX_RING + 2) * 8) + 16 + align16((size_t)kt * 8) + align16(TC_ROWS * 4) +
-           align16(TC_ROWS * 16) + align16(staging_floats * 4);
+    return align16((2 * MAX_RING + 2) * 8) + 16 + align16(TC_MAX_BIAS * 4) + align16((size_t)kt * 8) +
+           align16(TC_ROWS * 4) + align16(TC_ROWS * 16) + align16(staging_floats * 4);
 }
 
 static int tc_pick_ring(size_t base, int total_chunks)
@@ -983,6 +1007,12 @@ static int launch_tc(Kernel kern, const Params& p, dim3 grid, size_t bytes, cuda
 }  // namespace elo
 
 using namespace elo;
+
+extern "C" int elo_set_time_log(long long* device_buf)
+{
+    g_tlog = device_buf;
+    return ELO_OK;
+}
 
 extern "C" int elo_set_mlp_engine(int engine)
 {
@@ -1025,7 +1055,7 @@ extern "C" int elo_group_mlp_max(const elo_group_mlp_desc* d, void* stream)
         if (!d->feat2[u] || !d->weights[u] || !d->out[u] || !d->window[u].random_hw)
             return set_error(ELO_ERR_INVALID_ARGUMENT, "group_mlp_max: null pointer");
         p.feat2[s] = d->feat2[u]; p.random_hw[s] = d->window[u].random_hw; p.weights[s] = d->weights[u];
-        p.out[s] = d->out[u]; p.dbg_nbr[s] = d->dbg_nbr[u]; p.nbr_in[s] = d->nbr[u];
+        p.out[s] = d->out[u]; p.dbg_nbr[s] = d->dbg_nbr[u]; p.nbr_in[s] = d->nbr[u]; p.tlog = g_tlog;
         if (d->set_batch_offset[u] < 0) return set_error(ELO_ERR_INVALID_ARGUMENT, "group_mlp_max: negative batch offset");
         p.q_base[s] = (long long)d->set_batch_offset[u] * p.qs.oh * p.qs.ow;
         p.q_end[s] = p.q_base[s] + per_set;
@@ -1085,7 +1115,7 @@ extern "C" int elo_cost_volume_1(const elo_cost_volume_desc* d, void* stream)
     p.total_chunks = layer_chunks(xc, 128) + layer_chunks(128, 64) + layer_chunks(64, 64) + layer_chunks(10, 64) +
                      layer_chunks(128, 128) + layer_chunks(128, 64);
     p.xyz1 = d->xyz1; p.xyz2 = d->xyz2; p.f1 = d->f1; p.f2 = d->f2; p.random_hw = d->window_q.random_hw;
-    p.weights = d->weights_1; p.out = d->stage1_out; p.dbg_nbr = d->dbg_nbr_q; p.nbr_in = d->nbr_q;
+    p.weights = d->weights_1; p.out = d->stage1_out; p.dbg_nbr = d->dbg_nbr_q; p.nbr_in = d->nbr_q; p.tlog = g_tlog;
     const int kt = p.g.kt, xch = (xc + 3) & ~3;
     if (g_engine == 1) {
         if (!p.nbr_in) return set_error(ELO_ERR_INVALID_ARGUMENT, "cost_volume_1: the tensor-core engine takes nbr_q from elo_multi_search");
@@ -1142,7 +1172,7 @@ extern "C" int elo_cost_volume_2(const elo_cost_volume_desc* d, void* stream)
     p.C = d->C;
     p.total_chunks = layer_chunks(10, 64) + layer_chunks(128 + d->C, 128) + layer_chunks(128, 64);
     p.xyz1 = d->xyz1; p.f1 = d->f1; p.cv1 = d->stage1_out; p.random_hw = d->window_p.random_hw;
-    p.weights = d->weights_2; p.out = d->out; p.dbg_nbr = d->dbg_nbr_p; p.nbr_in = d->nbr_p;
+    p.weights = d->weights_2; p.out = d->out; p.dbg_nbr = d->dbg_nbr_p; p.nbr_in = d->nbr_p; p.tlog = g_tlog;
     const int kt = p.g.kt;
     if (g_engine == 1) {
         if (!p.nbr_in) return set_error(ELO_ERR_INVALID_ARGUMENT, "cost_volume_2: the tensor-core engine takes nbr_p from elo_multi_search");
@@ -1182,6 +1212,7 @@ extern "C" int elo_row_mlp(const elo_row_mlp_desc* d, void* stream)
         return set_error(ELO_ERR_INVALID_ARGUMENT, "row_mlp: bad arguments");
     if (d->rows == 0) return ELO_OK;
     RowMlpParams p;
+    p.tlog = g_tlog;
     p.rows = d->rows;
     p.nphase = d->num_phases;
     int chunks = 0, xmax = 0, prev_c = 0;

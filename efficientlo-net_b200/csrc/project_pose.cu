@@ -238,19 +238,42 @@ __global__ void __launch_bounds__(POSE_THREADS) pose_head_kernel(const PoseParam
     if (!s_last) return;
     __threadfence();
 
-    // last CTA of the sample: combine the partials, run the heads
-    if (threadIdx.x < 64) {
+    // last CTA of the sample: combine the partials (all 256 threads: 4 strided groups per channel,
+    // loads issued together), then run the heads
+    {
         const float* part = p.partial + (size_t)b * p.G * 192;
-        float M = -INFINITY;
-#pragma unroll 8
-        for (int g = 0; g < p.G; ++g) M = fmaxf(M, __ldcg(part + g * 192 + c));
+        float M = -INFINITY, S = 0.f, A = 0.f;
+        for (int g0 = sub; g0 < p.G; g0 += 4 * 8) {
+            float mg[8], sg[8], ag[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int g = g0 + 4 * u;
+                const bool in = g < p.G;
+                mg[u] = in ? __ldcg(part + g * 192 + c) : -INFINITY;
+                sg[u] = in ? __ldcg(part + g * 192 + 64 + c) : 0.f;
+                ag[u] = in ? __ldcg(part + g * 192 + 128 + c) : 0.f;
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                if (mg[u] == -INFINITY) continue;
+                const float Mn = fmaxf(M, mg[u]);
+                const float s0 = M == -INFINITY ? 0.f : expf(M - Mn), s1 = expf(mg[u] - Mn);
+                S = S * s0 + sg[u] * s1;
+                A = A * s0 + ag[u] * s1;
+                M = Mn;
+            }
+        }
+        __syncthreads();
+        s_m[sub][c] = M; s_s[sub][c] = S; s_a[sub][c] = A;
+        __syncthreads();
+    }
+    if (threadIdx.x < 64) {
+        float M = fmaxf(fmaxf(s_m[0][c], s_m[1][c]), fmaxf(s_m[2][c], s_m[3][c]));
         float S = 0.f, A = 0.f;
-#pragma unroll 4
-        for (int g = 0; g < p.G; ++g) {
-            const float mg = __ldcg(part + g * 192 + c);
-            const float sc = mg == -INFINITY ? 0.f : expf(mg - M);
-            S = fmaf(__ldcg(part + g * 192 + 64 + c), sc, S);
-            A = fmaf(__ldcg(part + g * 192 + 128 + c), sc, A);
+        for (int i = 0; i < 4; ++i) {
+            const float sc = s_m[i][c] == -INFINITY ? 0.f : expf(s_m[i][c] - M);
+            S = fmaf(s_s[i][c], sc, S);
+            A = fmaf(s_a[i][c], sc, A);
         }
         const float v = A / S;      // no valid point at all: 0/0 = NaN, as an empty softmax gives upstream
         s_pool[c] = v;

@@ -186,7 +186,7 @@ static int launch_small(const SmallParams& p, int nsets, cudaStream_t st)
     // <= 17 KB of weights from L2, which is cheap); many queries: 8 warps, grid-stride
     const long long sms = device_info().sm_count;
     long long wpc = (groups * nsets + 2 * sms - 1) / (2 * sms);
-    wpc = wpc < 1 ? 1 : (wpc > 8 ? 8 : wpc);
+    wpc = wpc < 4 ? 4 : (wpc > 8 ? 8 : wpc);      // at least 4 warps share a CTA's weight load
     long long ctas = (groups + wpc - 1) / wpc;
     const long long cap = sms * 4 / nsets;
     if (ctas > cap) ctas = cap;

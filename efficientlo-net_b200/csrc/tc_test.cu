@@ -82,7 +82,63 @@ __global__ void __launch_bounds__(256, 1) tc_dense_test_kernel(const float* __re
     if (warp == 0) tc::tmem_dealloc(tbase, tc::TMEM_COLS);
 }
 
+// Throughput probe: `iters` back-to-back MMAs (128 x N x 8, tf32) into one accumulator, A from TMEM (ts = 1) or
+// from shared memory (ts = 0); out[0] = SM cycles from first issue to completion.
+__global__ void __launch_bounds__(128, 1) tc_mma_bench_kernel(int N, int iters, int ts, int nacc, long long* out)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float* B = reinterpret_cast<float*>(smem_raw);            // [2][N][4]
+    float* A = B + 2 * 128 * 4;                               // [2][128][4] (SS form)
+    __shared__ uint64_t mbar;
+    __shared__ uint32_t tmem_base_s;
+    const int warp = threadIdx.x >> 5;
+    if (warp == 0) tc::tmem_alloc(&tmem_base_s, tc::TMEM_COLS);
+    if (threadIdx.x == 0) { mbar_init(&mbar, 1); mbar_fence_init(); }
+    for (int i = threadIdx.x; i < 4 * 128 * 4; i += blockDim.x) B[i] = 0.f;
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    const uint32_t tbase = tmem_base_s;
+    {   // zero the A columns in TMEM
+        uint32_t z[16];
+        for (int i = 0; i < 16; ++i) z[i] = 0u;
+        tc::tmem_st16(tbase + ((uint32_t)(32 * (warp & 3)) << 16), z);
+        tc::tmem_st_wait();
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        tc::fence_after_sync();
+        const uint32_t idesc = tc::idesc_tf32((uint32_t)N);
+        const uint64_t bdesc = tc::smem_desc(tc::smem_addr(B), (uint32_t)N * 16, 128);
+        const uint64_t adesc = tc::smem_desc(tc::smem_addr(A), 128 * 16, 128);
+        const long long t0 = clock64();
+        const uint32_t d0 = tbase + 128, d1 = d0 + (nacc > 1 ? N : 0), d2 = d0 + (nacc > 2 ? 2 * N : 0);
+        (void)adesc;
+        for (int i = 0; i < iters; i += 3) {          // three MMAs per trip, rotating over the accumulators
+            tc::mma_ts_c<true>(d0, tbase, bdesc, idesc);
+            tc::mma_ts_c<true>(d1, tbase + (ts ? 8 : 0), bdesc, idesc);
+            tc::mma_ts_c<true>(d2, tbase, bdesc, idesc);
+        }
+        tc::mma_commit(&mbar);
+        mbar_wait(&mbar, 0);
+        out[0] = clock64() - t0;
+    }
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc(tbase, tc::TMEM_COLS);
+}
+
 }  // namespace elo
+
+extern "C" int elo_tc_mma_bench(int N, int iters, int ts, int nacc, long long* out_cycles, void* stream)
+{
+    using namespace elo;
+    if (nacc < 1 || nacc * N > 384) return set_error(ELO_ERR_INVALID_ARGUMENT, "tc_mma_bench: nacc * N <= 384");
+    tc_mma_bench_kernel<<<1, 128, 16384, (cudaStream_t)stream>>>(N, iters, ts, nacc, out_cycles);
+    cudaError_t err = cudaGetLastError();
+    return err == cudaSuccess ? ELO_OK : set_cuda_error(err, "tc_mma_bench launch");
+}
 
 extern "C" int elo_tc_dense_test(const float* X, const float* W, const float* bias, float* Y, int K, int N, int relu,
                                  void* stream)

@@ -76,6 +76,9 @@ int elo_fused_conv_random_k(int batch_size, int H, int W, int npoints, int kerne
  * The packed `weights` a descriptor carries must match the engine (packing.pack_stream_tc / pack_stream). */
 int elo_set_mlp_engine(int engine);
 int elo_get_mlp_engine(void);
+/* Debug: device buffer of 64 int64; CTA (0,0) of every tensor-core kernel launched afterwards writes phase
+ * timestamps (ns, %globaltimer) into it: compute thread 0 -> [0,32), MMA thread -> [32,64).  NULL = off. */
+int elo_set_time_log(long long *device_buf);
 
 typedef struct {
     int kernel_size_H, kernel_size_W, K;
@@ -228,6 +231,9 @@ int elo_pose_head(const elo_pose_head_desc *desc, void *stream);
  * X, W, Y row-major on the device, K % 16 == 0, K <= 192, N in {64, 128}. */
 int elo_tc_dense_test(const float *X, const float *W, const float *bias, float *Y, int K, int N, int relu,
                       void *stream);
+
+/* Throughput probe: `iters` tf32 MMAs (128 x N x 8) rotating over `nacc` accumulators; out_cycles[0] (device) = SM cycles. */
+int elo_tc_mma_bench(int N, int iters, int ts, int nacc, long long *out_cycles, void *stream);
 
 /* Strided xyz pyramid (pwclo_model.py:88-114, get_selected_idx + gather_nd): level l of 4 keeps pixel
  * (i*stride_h[l], j*stride_w[l]) of xyz_in (samples,H,W,3) for i < out_h[l], j < out_w[l]; strides are
