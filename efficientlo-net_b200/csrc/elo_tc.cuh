@@ -25,6 +25,15 @@ constexpr uint32_t TMEM_COLS = 512;
 
 __device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// one lane of a fully converged warp (elect.sync): lets ptxas treat what follows as warp-uniform, so
+// tcgen05.mma is issued without a per-instruction ELECT / branch sequence
+__device__ __forceinline__ bool elect_one()
+{
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+
 // ---- TMEM allocation (one warp, all lanes) -------------------------------------------------------
 __device__ __forceinline__ void tmem_alloc(uint32_t* smem_holder, uint32_t ncols)
 {

@@ -40,13 +40,14 @@ struct TcPipe {
     uint32_t tbase;       // TMEM base address
     uint32_t layer;       // layers completed so far (parity of a_ready / done)
     uint32_t chunk;       // chunks consumed so far (MMA warp)
+    uint32_t cslot, cround;   // ring slot / lap of the next chunk (MMA warp)
     const float* bias;    // biases of the remaining layers, in shared memory (compute warps advance it)
     long long* tlog;      // optional phase timestamps (ns) of CTA (0,0): compute thread 0 -> [0,32), MMA thread -> [32,64)
 
     __device__ __forceinline__ void stamp(int id)
     {
-        if (tlog != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && (threadIdx.x & 31) == 0 &&
-            ((threadIdx.x >> 5) == 0 || (threadIdx.x >> 5) == COMPUTE_WARPS + 1)) {
+        if (tlog != nullptr && blockIdx.x == 0 && blockIdx.y == 0 &&
+            (threadIdx.x == 0 || (threadIdx.x >> 5) == COMPUTE_WARPS + 1)) {
             long long t;
             asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
             tlog[id + ((threadIdx.x >> 5) == 0 ? 0 : 32)] = t;
@@ -60,7 +61,7 @@ struct TcPipe {
         tlog = tlog_;
         stamp(0);
         ring = ring_; full = bars; empty = bars + MAX_RING; a_ready = bars + 2 * MAX_RING; done = a_ready + 1;
-        nring = nring_; layer = 0; chunk = 0; bias = bias_smem;
+        nring = nring_; layer = 0; chunk = 0; cslot = 0; cround = 0; bias = bias_smem;
         // every epilogue needs its biases at once: one L2 round trip here instead of one per layer
         for (int i = threadIdx.x; i < nbias; i += blockDim.x) bias_smem[i] = __ldg(bias_gmem + i);
         if (threadIdx.x == 0) {
@@ -87,12 +88,13 @@ struct TcPipe {
     // ---- TMA warp ------------------------------------------------------------------------------
     __device__ __forceinline__ void produce(const float* src, uint32_t total)
     {
-        if ((threadIdx.x & 31) != 0) return;
+        if (!tc::elect_one()) return;
+        uint32_t slot = 0, round = 0;
         for (uint32_t g = 0; g < total; ++g) {
-            const uint32_t slot = g % nring, round = g / nring;
             if (round > 0) mbar_wait(empty + slot, (round - 1) & 1u);
             mbar_expect_tx(full + slot, TC_CHUNK_BYTES);
             bulk_g2s(ring + (size_t)slot * TC_CHUNK_FLOATS, src + (size_t)g * TC_CHUNK_FLOATS, TC_CHUNK_BYTES, full + slot);
+            if (++slot == nring) { slot = 0; ++round; }
         }
     }
 
@@ -117,8 +119,8 @@ struct TcPipe {
         uint32_t a_hi = tbase + a_col;
         uint32_t ks = 0;
         while (ks < nks) {
-            const uint32_t slot = chunk % nring;
-            mbar_wait(full + slot, (chunk / nring) & 1u);
+            const uint32_t slot = cslot;
+            mbar_wait(full + slot, cround & 1u);
             tc::fence_after_sync();
             uint64_t bhi = desc0 + (uint64_t)slot * (TC_CHUNK_BYTES >> 4);
             uint64_t blo = bhi + (TC_CHUNK_BYTES >> 5);
@@ -134,6 +136,7 @@ struct TcPipe {
             }
             tc::mma_commit(empty + slot);              // slot reusable once these MMAs have read it
             ++chunk;
+            if (++cslot == nring) { cslot = 0; ++cround; }
         }
         tc::mma_commit(done);
         stamp(3 + 2 * (int)layer);

@@ -500,16 +500,112 @@ __device__ __forceinline__ TcSmem tc_carve(unsigned char* raw, int nring, int kt
     return m;
 }
 
+// Row layout of a tensor-core group tile: the K rows of a query never straddle a 32-row lane quarter, so
+// the reduction over the K neighbours is a warp shuffle among the K lanes that own them.
+//   gpw = 32 / K queries per quarter;  query ql -> rows (ql / gpw) * 32 + (ql % gpw) * K + k,  k < K.
+struct TcRows {
+    int K, gpw;
+    __device__ __forceinline__ explicit TcRows(int K_) : K(K_), gpw(32 / K_) {}
+    __device__ __forceinline__ int row(int ql, int k) const { return (ql / gpw) * 32 + (ql % gpw) * K + k; }
+    // query / neighbour of a row, or ql = -1 for the padding rows at the end of a quarter
+    __device__ __forceinline__ void decode(int r, int& ql, int& k) const
+    {
+        const int w = r & 31;
+        if (w >= gpw * K) { ql = -1; k = 0; return; }
+        ql = (r >> 5) * gpw + w / K;
+        k = w % K;
+    }
+};
+
+// nbr[row] / ctr[ql] of the tile from a pre-computed neighbour table (rows of padding / absent queries: -1)
+__device__ __forceinline__ void tc_load_nbr(const QuerySet& qs, const TcRows& rows, const float* __restrict__ xyz1,
+                                            const int* __restrict__ nbr_in, long long q0, int qt, long long total_q,
+                                            int* nbr, float* ctr)
+{
+    const int nq = qs.oh * qs.ow;
+    for (int r = threadIdx.x; r < TC_ROWS; r += CTA_THREADS) {
+        int ql, k;
+        rows.decode(r, ql, k);
+        nbr[r] = (ql >= 0 && ql < qt && q0 + ql < total_q) ? __ldg(nbr_in + (q0 + ql) * rows.K + k) : -1;
+    }
+    for (int ql = threadIdx.x; ql < TC_ROWS; ql += CTA_THREADS) {
+        const long long gq = q0 + ql;
+        float xc = 0.f, yc = 0.f, zc = 0.f;
+        int b = -1;
+        if (ql < qt && gq < total_q) {
+            int h, w;
+            b = (int)(gq / nq);
+            query_cell(qs, (int)(gq % nq), h, w);
+            const float* c = xyz1 + ((size_t)b * qs.H1 * qs.W1 + (size_t)h * qs.W1 + w) * 3;
+            xc = __ldg(c); yc = __ldg(c + 1); zc = __ldg(c + 2);
+        }
+        ctr[ql * 4 + 0] = xc; ctr[ql * 4 + 1] = yc; ctr[ql * 4 + 2] = zc;
+        ctr[ql * 4 + 3] = __int_as_float(b);
+    }
+}
+
+// centre / neighbour xyz of a row (zeros for masked neighbours and padding rows)
+__device__ __forceinline__ void tc_row_xyz(const TcRows& rows, int r, int qt, const int* nbr, const float* ctr,
+                                           const float* __restrict__ xyz2, int cells2, float (&p)[3], float (&q)[3])
+{
+    int ql, k;
+    rows.decode(r, ql, k);
+    p[0] = p[1] = p[2] = q[0] = q[1] = q[2] = 0.f;
+    if (ql < 0 || ql >= qt) return;
+    const int b = __float_as_int(ctr[ql * 4 + 3]);
+    if (b < 0) return;
+    p[0] = ctr[ql * 4 + 0]; p[1] = ctr[ql * 4 + 1]; p[2] = ctr[ql * 4 + 2];
+    const int cell = nbr[r];
+    if (cell >= 0) {
+        const float* s = xyz2 + ((size_t)b * cells2 + cell) * 3;
+        q[0] = __ldg(s); q[1] = __ldg(s + 1); q[2] = __ldg(s + 2);
+    }
+}
+
+// Pool staging: S[row][POOL_LD] with POOL_LD odd -> conflict-free both for the epilogue (lanes = consecutive
+// rows, one channel) and for the pooling tasks (lanes = consecutive channels, one row).
+constexpr int POOL_LD64 = 65;
+
+// masked softmax over the K rows of a query for one channel, applied to val (TF: where(mask, w, -1e10),
+// softmax(dim=2), reduce_sum(w * val)); an all-masked group gets uniform weights 1/K
+__device__ __forceinline__ float pool_softmax(const float* SL, const float* SV, int ld_v, const int* nbr, int r0, int K,
+                                              int c)
+{
+    // online form: one pass over the K rows.  __expf (ex2.approx) is accurate to ~1e-6 relative on the
+    // arguments (<= 0) seen here, two orders below the parity bar.
+    float m = -INFINITY, s = 0.f, a = 0.f;
+    for (int k = 0; k < K; ++k) {
+        const float l = nbr[r0 + k] >= 0 ? SL[(r0 + k) * POOL_LD64 + c] : -1e10f;
+        const float v = SV[(r0 + k) * ld_v + c];
+        if (l > m) {
+            const float sc = __expf(m - l);
+            s *= sc; a *= sc; m = l;
+        }
+        const float e = __expf(l - m);
+        s += e;
+        a = fmaf(e, v, a);
+    }
+    return a / s;
+}
+
 __global__ void __launch_bounds__(TC_LAUNCH_THREADS, 1) group_mlp_max_tc_kernel(const GroupMlpParams p)
 {
     constexpr int RS = TC_ROWS;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int cin0 = 3 + p.Cf;
     const int cout_last = p.cout[p.nl - 1];
-    const int stage_ch = max((cin0 + 3) & ~3, cout_last);
-    TcSmem sm = tc_carve(smem_raw, p.nring, p.g.kt, (size_t)stage_ch * RS);
+    const int pool_ld = cout_last + 1;
+    TcSmem sm = tc_carve(smem_raw, p.nring, p.g.kt, (size_t)max(((cin0 + 3) & ~3), pool_ld) * RS);
     const int set = blockIdx.y, warp = threadIdx.x >> 5;
     const Window g = p.g;
+    const TcRows rows(g.K);
+    int* nbr = sm.nbr; float* ctr = sm.ctr; float* X = sm.X;
+    const long long q0 = p.q_base[set] + (long long)blockIdx.x * p.qt;
+    const long long total_q = p.q_end[set];
+    const int cells2 = g.h2 * g.w2;
+    // neighbour table first: its global loads overlap the barrier / TMEM set-up below
+    if (warp < COMPUTE_WARPS && p.nbr_in[set] != nullptr)
+        tc_load_nbr(p.qs, rows, p.xyz1, p.nbr_in[set], q0, p.qt, total_q, nbr, ctr);
     TcPipe pipe;
     int nbias = 0;
     for (int l = 0; l < p.nl; ++l) nbias += p.cout[l];
@@ -517,72 +613,73 @@ __global__ void __launch_bounds__(TC_LAUNCH_THREADS, 1) group_mlp_max_tc_kernel(
               sm.bias, nbias, p.tlog);
     if (warp == COMPUTE_WARPS) { pipe.produce(p.weights[set], p.total_chunks); return; }
     if (warp == COMPUTE_WARPS + 1) {
-        if ((threadIdx.x & 31) == 0) {
+        if (tc::elect_one()) {
             int cin = cin0;
             for (int l = 0; l < p.nl; ++l) { pipe.issue_layer(0, cin, p.cout[l]); cin = p.cout[l]; }
         }
         return;
     }
-    int* nbr = sm.nbr; float* ctr = sm.ctr; float* X = sm.X;
-    if (p.nbr_in[set] == nullptr) build_offsets(sm.off, p.random_hw[set], g.kt, g.kH, g.kW, CTA_THREADS);
-    for (int i = threadIdx.x; i < RS; i += CTA_THREADS) nbr[i] = -1;
-    compute_sync();
-    const long long q0 = p.q_base[set] + (long long)blockIdx.x * p.qt;
-    const long long total_q = p.q_end[set];
-    const int cells2 = g.h2 * g.w2;
-    if (p.nbr_in[set] != nullptr) tile_load_nbr(p.qs, g.K, p.xyz1, p.nbr_in[set], q0, p.qt, total_q, nbr, ctr);
-    else tile_search<false>(p.qs, g, p.xyz1, p.xyz2, sm.off, q0, p.qt, total_q, nbr, ctr, nullptr, nullptr);
-    compute_sync();
-    for (int r = threadIdx.x; r < RS; r += CTA_THREADS) {
-        const int q = r / g.K;
-        float dx = 0.f, dy = 0.f, dz = 0.f;
-        if (q < p.qt) {
-            const int b = __float_as_int(ctr[q * 4 + 3]);
-            if (b >= 0) {
-                float qx = 0.f, qy = 0.f, qz = 0.f;
-                const int cell = nbr[r];
-                if (cell >= 0) {
-                    const float* s = p.xyz2 + ((size_t)b * cells2 + cell) * 3;
-                    qx = __ldg(s); qy = __ldg(s + 1); qz = __ldg(s + 2);
-                }
-                dx = qx - ctr[q * 4 + 0]; dy = qy - ctr[q * 4 + 1]; dz = qz - ctr[q * 4 + 2];
-            }
+    if (p.nbr_in[set] == nullptr) {
+        // stand-alone call without a table: search here, into a contiguous scratch, then re-lay the rows
+        build_offsets(sm.off, p.random_hw[set], g.kt, g.kH, g.kW, CTA_THREADS);
+        int* tmp = reinterpret_cast<int*>(X);
+        for (int i = threadIdx.x; i < RS; i += CTA_THREADS) tmp[i] = -1;
+        compute_sync();
+        tile_search<false>(p.qs, g, p.xyz1, p.xyz2, sm.off, q0, p.qt, total_q, tmp, ctr, nullptr, nullptr);
+        compute_sync();
+        for (int r = threadIdx.x; r < RS; r += CTA_THREADS) {
+            int ql, k;
+            rows.decode(r, ql, k);
+            nbr[r] = (ql >= 0 && ql < p.qt) ? tmp[ql * g.K + k] : -1;
         }
-        X[act_index(0, r, RS)] = dx; X[act_index(1, r, RS)] = dy; X[act_index(2, r, RS)] = dz;
+        compute_sync();
     }
-    {
-        const int K = g.K, qt = p.qt;
-        gather_features(X, RS, 3, p.feat2[set], p.Cf, RS, [&](int r) -> long long {
-            const int q = r / K;
-            if (q >= qt || nbr[r] < 0) return -1;
-            return (long long)__float_as_int(ctr[q * 4 + 3]) * cells2 + nbr[r];
-        });
+    for (int r = threadIdx.x; r < RS; r += CTA_THREADS) {
+        float pc[3], qc[3];
+        tc_row_xyz(rows, r, p.qt, nbr, ctr, p.xyz2, cells2, pc, qc);
+        X[act_index(0, r, RS)] = qc[0] - pc[0];
+        X[act_index(1, r, RS)] = qc[1] - pc[1];
+        X[act_index(2, r, RS)] = qc[2] - pc[2];
     }
+    gather_features(X, RS, 3, p.feat2[set], p.Cf, RS, [&](int r) -> long long {
+        int ql, k;
+        rows.decode(r, ql, k);
+        if (ql < 0 || ql >= p.qt || nbr[r] < 0) return -1;
+        return (long long)__float_as_int(ctr[ql * 4 + 3]) * cells2 + nbr[r];
+    });
     compute_sync();
     pipe.load_a_from_smem(X, 0, cin0, 0);
     pipe.signal_a_ready();
+    const int m = pipe.my_row();
+    float* S = X;                                // staging reused as S[row][cout_last + 1]: X is dead once loaded
     for (int l = 0; l < p.nl; ++l) {
         const bool last = l == p.nl - 1;
         pipe.epilogue<true>(p.cout[l], [&](int b, const float (&v)[16]) {
-            if (last) pipe.store_smem(X, 0, b, v);       // X is dead: every thread loaded its row before layer 0 ran
-            else pipe.store_a(0, b, v);
+            if (!last) { pipe.store_a(0, b, v); return; }
+#pragma unroll
+            for (int i = 0; i < 16; ++i) S[m * pool_ld + b * 16 + i] = v[i];
         });
         if (!last) pipe.signal_a_ready();
     }
     compute_sync();
+    // max over the K neighbours of (y * mask): y >= 0 after ReLU, masked rows count as 0
     float* out = p.out[set];
     for (int t = threadIdx.x; t < p.qt * cout_last; t += CTA_THREADS) {
-        const int q = t / cout_last, c = t - q * cout_last;
-        const long long gq = q0 + q;
+        const int ql = t / cout_last, c = t - ql * cout_last;
+        const long long gq = q0 + ql;
         if (gq >= total_q) break;
-        float m = 0.f;
+        const int r0 = rows.row(ql, 0);
+        float mx = 0.f;
         for (int k = 0; k < g.K; ++k)
-            if (nbr[q * g.K + k] >= 0) m = fmaxf(m, X[act_index(c, q * g.K + k, RS)]);
-        out[gq * cout_last + c] = m;
+            if (nbr[r0 + k] >= 0) mx = fmaxf(mx, S[(r0 + k) * pool_ld + c]);
+        out[gq * cout_last + c] = mx;
     }
     if (p.dbg_nbr[set] != nullptr)
-        for (int t = threadIdx.x; t < p.qt * g.K; t += CTA_THREADS)
-            if (q0 + t / g.K < total_q) p.dbg_nbr[set][q0 * g.K + t] = nbr[t];
+        for (int r = threadIdx.x; r < RS; r += CTA_THREADS) {
+            int q2, k2;
+            rows.decode(r, q2, k2);
+            if (q2 >= 0 && q2 < p.qt && q0 + q2 < total_q) p.dbg_nbr[set][(q0 + q2) * g.K + k2] = nbr[r];
+        }
     pipe.finish();
 }
 
@@ -591,16 +688,20 @@ __global__ void __launch_bounds__(TC_LAUNCH_THREADS, 1) cost_volume_1_tc_kernel(
     constexpr int RS = TC_ROWS;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int C = p.C, xc = 10 + 2 * C;
-    const int stage_ch = max((xc + 3) & ~3, 128);
-    TcSmem sm = tc_carve(smem_raw, p.nring, p.g.kt, (size_t)stage_ch * RS);
+    TcSmem sm = tc_carve(smem_raw, p.nring, 0, (size_t)max(((xc + 3) & ~3), 2 * POOL_LD64) * RS);
     const int warp = threadIdx.x >> 5;
     const Window g = p.g;
+    const TcRows rows(g.K);
+    int* nbr = sm.nbr; float* ctr = sm.ctr; float* X = sm.X;
+    const long long q0 = (long long)blockIdx.x * p.qt;
+    const int cells = g.h2 * g.w2;
+    if (warp < COMPUTE_WARPS) tc_load_nbr(p.qs, rows, p.xyz1, p.nbr_in, q0, p.qt, p.total_q, nbr, ctr);
     TcPipe pipe;
     pipe.init(sm.ring, sm.bars, p.nring, sm.tmem_holder, p.weights + (size_t)p.total_chunks * TC_CHUNK_FLOATS,
               sm.bias, 128 + 64 + 64 + 64 + 128 + 64, p.tlog);
     if (warp == COMPUTE_WARPS) { pipe.produce(p.weights, p.total_chunks); return; }
     if (warp == COMPUTE_WARPS + 1) {
-        if ((threadIdx.x & 31) == 0) {
+        if (tc::elect_one()) {
             pipe.issue_layer(0, xc, 128);     // CV_0
             pipe.issue_layer(0, 128, 64);     // CV_1
             pipe.issue_layer(0, 64, 64);      // CV_2      -> F
@@ -610,64 +711,49 @@ __global__ void __launch_bounds__(TC_LAUNCH_THREADS, 1) cost_volume_1_tc_kernel(
         }
         return;
     }
-    int* nbr = sm.nbr; float* ctr = sm.ctr; float* X = sm.X;
-    for (int i = threadIdx.x; i < RS; i += CTA_THREADS) nbr[i] = -1;
-    compute_sync();
-    const long long q0 = (long long)blockIdx.x * p.qt;
-    const int cells = g.h2 * g.w2;
-    // this kernel takes its neighbour table from elo_multi_search (the launcher guarantees nbr_in)
-    tile_load_nbr(p.qs, g.K, p.xyz1, p.nbr_in, q0, p.qt, p.total_q, nbr, ctr);
-    compute_sync();
     pipe.stamp(2);
     for (int r = threadIdx.x; r < RS; r += CTA_THREADS) {
-        const int q = r / g.K;
-        float px = 0.f, py = 0.f, pz = 0.f, qx = 0.f, qy = 0.f, qz = 0.f;
-        if (q < p.qt) {
-            const int b = __float_as_int(ctr[q * 4 + 3]);
-            if (b >= 0) {
-                px = ctr[q * 4 + 0]; py = ctr[q * 4 + 1]; pz = ctr[q * 4 + 2];
-                const int cell = nbr[r];
-                if (cell >= 0) {
-                    const float* s = p.xyz2 + ((size_t)b * cells + cell) * 3;
-                    qx = __ldg(s); qy = __ldg(s + 1); qz = __ldg(s + 2);
-                }
-            }
-        }
-        write_xyz10(X, RS, r, px, py, pz, qx, qy, qz);
+        float pc[3], qc[3];
+        tc_row_xyz(rows, r, p.qt, nbr, ctr, p.xyz2, cells, pc, qc);
+        write_xyz10(X, RS, r, pc[0], pc[1], pc[2], qc[0], qc[1], qc[2]);
     }
     {
-        const int K = g.K, qt = p.qt, nq = p.qs.oh * p.qs.ow;
+        const int qt = p.qt, nq = p.qs.oh * p.qs.ow;
         const long long total = p.total_q;
+        // f1 of the query pixel, repeated for its K rows (queries are all pixels: linear cell = gq)
         gather_features(X, RS, 10, p.f1, C, RS, [&](int r) -> long long {
-            const int q = r / K;
-            return (q < qt && q0 + q < total) ? q0 + q : -1;
+            int ql, k;
+            rows.decode(r, ql, k);
+            return (ql >= 0 && ql < qt && q0 + ql < total) ? q0 + ql : -1;
         });
         gather_features(X, RS, 10 + C, p.f2, C, RS, [&](int r) -> long long {
-            const int q = r / K;
-            if (q >= qt || nbr[r] < 0) return -1;
-            return (long long)((q0 + q) / nq) * cells + nbr[r];
+            int ql, k;
+            rows.decode(r, ql, k);
+            if (ql < 0 || ql >= qt || nbr[r] < 0) return -1;
+            return (long long)((q0 + ql) / nq) * cells + nbr[r];
         });
     }
     compute_sync();
     pipe.stamp(3);
+    const int m = pipe.my_row();
     // the 10 xyz channels are needed again by CV_xyz after the tile's A region has been overwritten
     float x10[16];
-    {
-        const int m = pipe.my_row();
 #pragma unroll
-        for (int i = 0; i < 16; ++i) x10[i] = i < 10 ? X[act_index(i, m, RS)] : 0.f;
-    }
+    for (int i = 0; i < 16; ++i) x10[i] = i < 10 ? X[act_index(i, m, RS)] : 0.f;
     pipe.load_a_from_smem(X, 0, xc, 0);
     pipe.signal_a_ready();
     pipe.stamp(4);
-    float* S = X;                               // staging reused: F at channels [0,64), logits at [64,128)
+    // pool staging (the X region is dead once every thread has loaded its row): F and logits as [row][65]
+    float* SF = X;
+    float* SL = X + RS * POOL_LD64;
     pipe.epilogue<true>(128, [&](int b, const float (&v)[16]) { pipe.store_a(0, b, v); });        // CV_0
     pipe.signal_a_ready();
     pipe.epilogue<true>(64, [&](int b, const float (&v)[16]) { pipe.store_a(0, b, v); });         // CV_1
     pipe.signal_a_ready();
     pipe.epilogue<true>(64, [&](int b, const float (&v)[16]) {                                    // CV_2 = F
         pipe.store_a(64, b, v);
-        pipe.store_smem(S, 0, b, v);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) SF[m * POOL_LD64 + b * 16 + i] = v[i];
     });
     if (pipe.my_half() == 0) {                  // re-materialise the xyz block for CV_xyz
         uint32_t hi[16], lo[16];
@@ -681,19 +767,25 @@ __global__ void __launch_bounds__(TC_LAUNCH_THREADS, 1) cost_volume_1_tc_kernel(
     pipe.signal_a_ready();
     pipe.epilogue<true>(128, [&](int b, const float (&v)[16]) { pipe.store_a(0, b, v); });        // sum_CV_0
     pipe.signal_a_ready();
-    pipe.epilogue<true>(64, [&](int b, const float (&v)[16]) { pipe.store_smem(S, 64, b, v); });  // logits
+    pipe.epilogue<true>(64, [&](int b, const float (&v)[16]) {                                    // logits
+#pragma unroll
+        for (int i = 0; i < 16; ++i) SL[m * POOL_LD64 + b * 16 + i] = v[i];
+    });
     compute_sync();
     pipe.stamp(5);
     for (int t = threadIdx.x; t < p.qt * 64; t += CTA_THREADS) {
-        const int q = t >> 6, c = t & 63;
-        const long long gq = q0 + q;
+        const int ql = t >> 6, c = t & 63;
+        const long long gq = q0 + ql;
         if (gq >= p.total_q) break;
-        p.out[gq * 64 + c] = softmax_pool(S + 64 * RS, S, nbr + q * g.K, c, q * g.K, g.K, RS);
+        p.out[gq * 64 + c] = pool_softmax(SL, SF, POOL_LD64, nbr, rows.row(ql, 0), g.K, c);
     }
     pipe.stamp(6);
     if (p.dbg_nbr != nullptr)
-        for (int t = threadIdx.x; t < p.qt * g.K; t += CTA_THREADS)
-            if (q0 + t / g.K < p.total_q) p.dbg_nbr[q0 * g.K + t] = nbr[t];
+        for (int r = threadIdx.x; r < RS; r += CTA_THREADS) {
+            int q2, k2;
+            rows.decode(r, q2, k2);
+            if (q2 >= 0 && q2 < p.qt && q0 + q2 < p.total_q) p.dbg_nbr[(q0 + q2) * g.K + k2] = nbr[r];
+        }
     pipe.finish();
     pipe.stamp(7);
 }
@@ -703,88 +795,78 @@ __global__ void __launch_bounds__(TC_LAUNCH_THREADS, 1) cost_volume_2_tc_kernel(
     constexpr int RS = TC_ROWS;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int C = p.C;
-    // staging channels: [0,10) xyz, [16,16+C) f1, [16+C,80+C) stage-1 of the neighbour, [80+C,144+C) logits
-    TcSmem sm = tc_carve(smem_raw, p.nring, p.g.kt, (size_t)(144 + C) * RS);
+    // staging channels: [0,10) xyz, [16,16+C) f1, [16+C,80+C) stage-1 features of the neighbour; then the pool
+    // staging SV / SL as [row][65]
+    TcSmem sm = tc_carve(smem_raw, p.nring, 0, (size_t)(80 + C + 2 * POOL_LD64) * RS);
     const int warp = threadIdx.x >> 5;
     const Window g = p.g;
+    const TcRows rows(g.K);
+    int* nbr = sm.nbr; float* ctr = sm.ctr; float* X = sm.X;
+    const long long q0 = (long long)blockIdx.x * p.qt;
+    const int cells = g.h2 * g.w2;
+    if (warp < COMPUTE_WARPS) tc_load_nbr(p.qs, rows, p.xyz1, p.nbr_in, q0, p.qt, p.total_q, nbr, ctr);
     TcPipe pipe;
     pipe.init(sm.ring, sm.bars, p.nring, sm.tmem_holder, p.weights + (size_t)p.total_chunks * TC_CHUNK_FLOATS,
               sm.bias, 64 + 128 + 64, p.tlog);
     if (warp == COMPUTE_WARPS) { pipe.produce(p.weights, p.total_chunks); return; }
     if (warp == COMPUTE_WARPS + 1) {
-        if ((threadIdx.x & 31) == 0) {
+        if (tc::elect_one()) {
             pipe.issue_layer(0, 10, 64);          // sum_xyz_encoding
             pipe.issue_layer(0, 128 + C, 128);    // sum_cost_volume_0 on [enc | f1 | stage-1]
             pipe.issue_layer(0, 128, 64);         // sum_cost_volume_1 -> logits
         }
         return;
     }
-    int* nbr = sm.nbr; float* ctr = sm.ctr; float* X = sm.X;
-    for (int i = threadIdx.x; i < RS; i += CTA_THREADS) nbr[i] = -1;
-    compute_sync();
-    const long long q0 = (long long)blockIdx.x * p.qt;
-    const int cells = g.h2 * g.w2;
-    tile_load_nbr(p.qs, g.K, p.xyz1, p.nbr_in, q0, p.qt, p.total_q, nbr, ctr);
-    compute_sync();
     for (int r = threadIdx.x; r < RS; r += CTA_THREADS) {
-        const int q = r / g.K;
-        float px = 0.f, py = 0.f, pz = 0.f, qx = 0.f, qy = 0.f, qz = 0.f;
-        if (q < p.qt) {
-            const int b = __float_as_int(ctr[q * 4 + 3]);
-            if (b >= 0) {
-                px = ctr[q * 4 + 0]; py = ctr[q * 4 + 1]; pz = ctr[q * 4 + 2];
-                const int cell = nbr[r];
-                if (cell >= 0) {
-                    const float* s = p.xyz1 + ((size_t)b * cells + cell) * 3;
-                    qx = __ldg(s); qy = __ldg(s + 1); qz = __ldg(s + 2);
-                }
-            }
-        }
-        write_xyz10(X, RS, r, px, py, pz, qx, qy, qz);
+        float pc[3], qc[3];
+        tc_row_xyz(rows, r, p.qt, nbr, ctr, p.xyz1, cells, pc, qc);
+        write_xyz10(X, RS, r, pc[0], pc[1], pc[2], qc[0], qc[1], qc[2]);
     }
     {
-        const int K = g.K, qt = p.qt, nq = p.qs.oh * p.qs.ow;
+        const int qt = p.qt, nq = p.qs.oh * p.qs.ow;
         const long long total = p.total_q;
         gather_features(X, RS, 16, p.f1, C, RS, [&](int r) -> long long {
-            const int q = r / K;
-            return (q < qt && q0 + q < total) ? q0 + q : -1;
+            int ql, k;
+            rows.decode(r, ql, k);
+            return (ql >= 0 && ql < qt && q0 + ql < total) ? q0 + ql : -1;
         });
         gather_features(X, RS, 16 + C, p.cv1, 64, RS, [&](int r) -> long long {
-            const int q = r / K;
-            if (q >= qt || nbr[r] < 0) return -1;
-            return (long long)((q0 + q) / nq) * cells + nbr[r];
+            int ql, k;
+            rows.decode(r, ql, k);
+            if (ql < 0 || ql >= qt || nbr[r] < 0) return -1;
+            return (long long)((q0 + ql) / nq) * cells + nbr[r];
         });
     }
     compute_sync();
     pipe.load_a_from_smem(X, 0, 10, 0);
     pipe.load_a_from_smem(X, 16, C + 64, 64);
     pipe.signal_a_ready();
+    const int m = pipe.my_row();
+    float* SV = X + (size_t)(80 + C) * RS;
+    float* SL = SV + RS * POOL_LD64;
+    // while the first MMAs run: this row's gathered stage-1 features into the pooling layout (masked rows hold 0)
+    for (int c = pipe.my_half() * 32; c < pipe.my_half() * 32 + 32; ++c) SV[m * POOL_LD64 + c] = X[act_index(16 + C + c, m, RS)];
     pipe.epilogue<true>(64, [&](int b, const float (&v)[16]) { pipe.store_a(0, b, v); });         // enc
     pipe.signal_a_ready();
     pipe.epilogue<true>(128, [&](int b, const float (&v)[16]) { pipe.store_a(0, b, v); });
     pipe.signal_a_ready();
-    pipe.epilogue<true>(64, [&](int b, const float (&v)[16]) { pipe.store_smem(X, 80 + C, b, v); });
+    pipe.epilogue<true>(64, [&](int b, const float (&v)[16]) {                                    // logits
+#pragma unroll
+        for (int i = 0; i < 16; ++i) SL[m * POOL_LD64 + b * 16 + i] = v[i];
+    });
     compute_sync();
     for (int t = threadIdx.x; t < p.qt * 64; t += CTA_THREADS) {
-        const int q = t >> 6, c = t & 63;
-        const long long gq = q0 + q;
+        const int ql = t >> 6, c = t & 63;
+        const long long gq = q0 + ql;
         if (gq >= p.total_q) break;
-        const int* nrow = nbr + q * g.K;
-        float m = -INFINITY;
-        for (int k = 0; k < g.K; ++k)
-            m = fmaxf(m, nrow[k] >= 0 ? X[act_index(80 + C + c, q * g.K + k, RS)] : -1e10f);
-        float s = 0.f, acc = 0.f;
-        for (int k = 0; k < g.K; ++k) {
-            const float l = nrow[k] >= 0 ? X[act_index(80 + C + c, q * g.K + k, RS)] : -1e10f;
-            const float e = expf(l - m);
-            s += e;
-            acc = fmaf(e, X[act_index(16 + C + c, q * g.K + k, RS)], acc);
-        }
-        p.out[gq * 64 + c] = acc / s;
+        p.out[gq * 64 + c] = pool_softmax(SL, SV, POOL_LD64, nbr, rows.row(ql, 0), g.K, c);
     }
     if (p.dbg_nbr != nullptr)
-        for (int t = threadIdx.x; t < p.qt * g.K; t += CTA_THREADS)
-            if (q0 + t / g.K < p.total_q) p.dbg_nbr[q0 * g.K + t] = nbr[t];
+        for (int r = threadIdx.x; r < RS; r += CTA_THREADS) {
+            int q2, k2;
+            rows.decode(r, q2, k2);
+            if (q2 >= 0 && q2 < p.qt && q0 + q2 < p.total_q) p.dbg_nbr[(q0 + q2) * g.K + k2] = nbr[r];
+        }
     pipe.finish();
 }
 
@@ -802,7 +884,7 @@ __global__ void __launch_bounds__(TC_LAUNCH_THREADS, 1) row_mlp_tc_kernel(const 
               sm.bias, nbias, p.tlog);
     if (warp == COMPUTE_WARPS) { pipe.produce(p.weights[set], p.total_chunks); return; }
     if (warp == COMPUTE_WARPS + 1) {
-        if ((threadIdx.x & 31) == 0)
+        if (tc::elect_one())
             for (int ph = 0; ph < p.nphase; ++ph) {
                 int cin = 0;
                 for (int i = 0; i < p.nsrc[ph]; ++i) cin += p.src_c[ph][i];
@@ -967,7 +1049,8 @@ struct TcChoice { int per_tile, tiles; };
 static TcChoice choose_tc_tile(long long units, int rows_per_unit, int nsets)
 {
     const int sms = device_info().sm_count;
-    const int cap = TC_ROWS / rows_per_unit;
+    // a query's rows never straddle a 32-row lane quarter (TcRows): 4 * floor(32 / K) queries per tile
+    const int cap = rows_per_unit > 1 ? 4 * (32 / rows_per_unit) : TC_ROWS;
     long long tiles = (units + cap - 1) / cap;
     const long long waves = (tiles * nsets + sms - 1) / sms;
     long long slots = waves * sms / nsets;
@@ -1062,12 +1145,12 @@ extern "C" int elo_group_mlp_max(const elo_group_mlp_desc* d, void* stream)
     }
     const int kt = p.g.kt, xch = (3 + p.Cf + 3) & ~3;
     if (g_engine == 1) {
-        if (p.g.K > TC_ROWS) return set_error(ELO_ERR_UNSUPPORTED, "group_mlp_max: K > 128");
+        if (p.g.K > 32) return set_error(ELO_ERR_UNSUPPORTED, "group_mlp_max: the tensor-core engine takes K <= 32");
         int cin_t = 3 + p.Cf, chunks_t = 0;
         for (int l = 0; l < p.nl; ++l) { chunks_t += tc_layer_chunks(cin_t, p.cout[l]); cin_t = p.cout[l]; }
         p.total_chunks = chunks_t;
-        const int stage_ch = xch > p.cout[p.nl - 1] ? xch : p.cout[p.nl - 1];
-        const size_t base = tc_base_smem(kt, (size_t)stage_ch * TC_ROWS);
+        const int pool_ld = p.cout[p.nl - 1] + 1;
+        const size_t base = tc_base_smem(kt, (size_t)(xch > pool_ld ? xch : pool_ld) * TC_ROWS);
         p.nring = tc_pick_ring(base, chunks_t);
         if (p.nring < 2) return set_error(ELO_ERR_UNSUPPORTED, "group_mlp_max: tile does not fit shared memory");
         const TcChoice tc = choose_tc_tile(per_set, p.g.K, d->nsets);
@@ -1121,8 +1204,8 @@ extern "C" int elo_cost_volume_1(const elo_cost_volume_desc* d, void* stream)
         if (!p.nbr_in) return set_error(ELO_ERR_INVALID_ARGUMENT, "cost_volume_1: the tensor-core engine takes nbr_q from elo_multi_search");
         p.total_chunks = tc_layer_chunks(xc, 128) + tc_layer_chunks(128, 64) + tc_layer_chunks(64, 64) +
                          tc_layer_chunks(10, 64) + tc_layer_chunks(128, 128) + tc_layer_chunks(128, 64);
-        const int stage_ch = xch > 128 ? xch : 128;
-        const size_t base = tc_base_smem(0, (size_t)stage_ch * TC_ROWS);
+        if (p.g.K > 32) return set_error(ELO_ERR_UNSUPPORTED, "cost_volume_1: the tensor-core engine takes nsample_q <= 32");
+        const size_t base = tc_base_smem(0, (size_t)(xch > 130 ? xch : 130) * TC_ROWS);
         p.nring = tc_pick_ring(base, p.total_chunks);
         if (p.nring < 2) return set_error(ELO_ERR_UNSUPPORTED, "cost_volume_1: tile does not fit shared memory");
         const TcChoice tc = choose_tc_tile(p.total_q, p.g.K, 1);
@@ -1177,7 +1260,8 @@ extern "C" int elo_cost_volume_2(const elo_cost_volume_desc* d, void* stream)
     if (g_engine == 1) {
         if (!p.nbr_in) return set_error(ELO_ERR_INVALID_ARGUMENT, "cost_volume_2: the tensor-core engine takes nbr_p from elo_multi_search");
         p.total_chunks = tc_layer_chunks(10, 64) + tc_layer_chunks(128 + d->C, 128) + tc_layer_chunks(128, 64);
-        const size_t base = tc_base_smem(0, (size_t)(144 + d->C) * TC_ROWS);
+        if (p.g.K > 32) return set_error(ELO_ERR_UNSUPPORTED, "cost_volume_2: the tensor-core engine takes nsample <= 32");
+        const size_t base = tc_base_smem(0, (size_t)(80 + d->C + 130) * TC_ROWS);
         p.nring = tc_pick_ring(base, p.total_chunks);
         if (p.nring < 2) return set_error(ELO_ERR_UNSUPPORTED, "cost_volume_2: tile does not fit shared memory");
         const TcChoice tc = choose_tc_tile(p.total_q, p.g.K, 1);

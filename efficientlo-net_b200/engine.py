@@ -75,3 +75,68 @@ class PWCLOEngine:
             q, t = out[0].to("cpu", non_blocking=True), out[1].to("cpu", non_blocking=True)
         self.stream.synchronize()
         return q, t
+
+
+class PWCLOPipeline:
+    """Streaming inference from host memory: while one captured forward runs, the next batch is uploaded
+    on a copy stream (two engine instances = two input buffers + two graphs, alternating).  Every batch
+    still pays its own host->device copy and device->host read of (q, t); they just overlap the compute
+    of the neighbouring batches, as a deployment that consumes a LiDAR stream would run it."""
+
+    def __init__(self, batch_size, H_input=64, W_input=1800, num_points=150000, params=None, perms=None,
+                 device="cuda:0", depth=2):
+        self.device = torch.device(device)
+        store = params if isinstance(params, ParamStore) else ParamStore(
+            params if params is not None else init_params(0), self.device)
+        self.engines = [PWCLOEngine(batch_size, H_input, W_input, num_points, params=store, perms=perms,
+                                    device=device).capture() for _ in range(depth)]
+        self.copy_stream = torch.cuda.Stream(self.device)
+        self.compute_stream = torch.cuda.Stream(self.device)
+        self.uploaded = [torch.cuda.Event() for _ in range(depth)]
+        self.consumed = [torch.cuda.Event() for _ in range(depth)]
+        self.results = [(torch.empty(batch_size, 4).pin_memory(), torch.empty(batch_size, 3).pin_memory())
+                        for _ in range(depth)]
+        self.done = [torch.cuda.Event() for _ in range(depth)]
+        for e in self.consumed:
+            e.record(self.compute_stream)
+
+    def _upload(self, slot, pc, T_gt):
+        eng = self.engines[slot]
+        with torch.cuda.stream(self.copy_stream):
+            self.copy_stream.wait_event(self.consumed[slot])      # the previous forward on this slot has read its input
+            eng.pc.copy_(pc, non_blocking=True)
+            if T_gt is not None:
+                eng.T_gt.copy_(T_gt, non_blocking=True)
+            self.uploaded[slot].record(self.copy_stream)
+
+    def _compute(self, slot):
+        eng = self.engines[slot]
+        with torch.cuda.stream(self.compute_stream):
+            self.compute_stream.wait_event(self.uploaded[slot])
+            eng.graph.replay()
+            self.consumed[slot].record(self.compute_stream)
+            q, t = self.results[slot]
+            q.copy_(eng.outputs[0], non_blocking=True)
+            t.copy_(eng.outputs[1], non_blocking=True)
+            self.done[slot].record(self.compute_stream)
+
+    def run(self, batches):
+        """batches: iterable of (point_cloud (B,2N,6) pinned host tensor, T_gt or None).  Yields (q, t) host
+        tensors per batch, in order (each valid until `depth` more batches have been consumed)."""
+        depth = len(self.engines)
+        pending = []
+        it = iter(batches)
+        i = 0
+        for pc, T in it:
+            slot = i % depth
+            if len(pending) == depth:
+                s = pending.pop(0)
+                self.done[s].synchronize()
+                yield self.results[s]
+            self._upload(slot, pc, T)
+            self._compute(slot)
+            pending.append(slot)
+            i += 1
+        for s in pending:
+            self.done[s].synchronize()
+            yield self.results[s]

@@ -12,6 +12,7 @@ import math
 
 import torch
 
+from . import _lib
 from . import model_util as mu
 from . import pointnet_util as pu
 from .params import make_perms
@@ -132,6 +133,7 @@ def get_model(point_cloud, H_input, W_input, T_gt, T_trans, T_trans_inv, is_trai
         pts = [None] * 4
         src_xyz, src_pts, src_c = xyz_in, None, 3
         for l in range(4):
+            _lib.PROFILE_TAG[0] = "sa%d" % l
             sel = sels[l]
             scopes = ["sa1/layer%d/conv%d" % (l, j) for j in range(3)]
             feat = pu.set_conv(src_xyz, src_pts, sel, DOWN_CFG[l][0], DOWN_CFG[l][1], DOWN_CONV_DIS[l], scopes, store,
@@ -152,10 +154,12 @@ def get_model(point_cloud, H_input, W_input, T_gt, T_trans, T_trans_inv, is_trai
             return t.reshape(t.shape[0], oh[l + 2], ow[l + 2], -1)
 
         # ---- initial cost volume on level 2 and its set-conv to level 3 (:170-178)
+        _lib.PROFILE_TAG[0] = "l2o"
         l2_new = pu.cost_volume(f1(xyz[2]), f2(xyz[2]), grid(2, f1(pts[2])), grid(2, f2(pts[2])), [3, 5], [5, 35],
                                 4, 32, COST_VOLUME_DIS[2], [128, 64, 64], [128, 64], False, bn_decay,
                                 "flow_embedding_l2_origin", random_hw_q=perms["flow_embedding_l2_origin/q"],
                                 random_hw_p=perms["flow_embedding_l2_origin/p"], nbr_q=nbr_l2o_q, nbr_p=nbr_l2o_p)
+        _lib.PROFILE_TAG[0] = "l3"
         l3_cv = pu.set_conv(f1(xyz[2]), grid(2, l2_new), sel3, 16, (5, 9), DOWN_CONV_DIS[3],
                             ["new_layer3/conv%d" % j for j in range(3)], store, [perms["new_layer3"]], nbr=nbr_new3)
         # ---- level 3: embedding mask, attention pooling, coarse pose (:181-208)
@@ -171,6 +175,7 @@ def get_model(point_cloud, H_input, W_input, T_gt, T_trans, T_trans_inv, is_trai
         up_xyz = f1(xyz[3])                 # level 2 up-samples from the UN-warped level-3 grid (:247)
         up_w, up_pred = grid(3, l3_w), grid(3, l3_cv)
         for lvl in (2, 1, 0):
+            _lib.PROFILE_TAG[0] = "l%d" % lvl
             h, w_ = oh[lvl + 2], ow[lvl + 2]
             C = pts[lvl].shape[-1]
             # warp with the coarse pose and re-project (:213-237): one fused pass
@@ -220,6 +225,7 @@ def get_model(point_cloud, H_input, W_input, T_gt, T_trans, T_trans_inv, is_trai
             q_norm[lvl], t_lvl[lvl] = pose["q_norm"], t
             up_xyz, up_w, up_pred = xyz_wp, wgt.view(B, h, w_, 64), pred.view(B, h, w_, 64)
 
+    _lib.PROFILE_TAG[0] = ""
     l0_xyz_f1 = f1(xyz[0]).reshape(B, -1, 3)
     return (q_norm[0], t_lvl[0], q_norm[1], t_lvl[1], q_norm[2], t_lvl[2], q_norm[3], t_lvl[3], l0_xyz_f1,
             q_gt, t_gt)
