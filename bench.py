@@ -34,6 +34,19 @@ POOL_BYTES = 144e6          # distinct input batches rotated through the timed l
 METRIC = "frame-pairs/sec on 64x1800 synthetic KITTI scans; cost-volume HBM GB/s vs roofline"
 
 
+def profiled_traffic(kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch of `kernel` from the committed ncu --set full
+    capture (profiles/traffic_r*.json, written by the profiling pass; B = 1), or None."""
+    import glob
+    best = None
+    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "traffic_r*.json"))):
+        try:
+            best = json.load(open(path)).get("dram_bytes_per_launch", {}).get(kernel, best)
+        except Exception:
+            pass
+    return best
+
+
 def measured_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -59,7 +72,7 @@ class ClockSampler(threading.Thread):
                 self.rows.append([x.strip() for x in out.strip().split(",")])
             except Exception:
                 pass
-            self.stop_flag.wait(0.2)
+            self.stop_flag.wait(0.05)
 
     def summary(self):
         self.stop_flag.set()
@@ -301,7 +314,8 @@ def run_ours(args, rank, world, local_rank):
             tf = flops / dur / 1e12
             roof = {"kernel": "%s[%s]" % (name, tag), "bound": "tensor", "achieved": tf,
                     "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": tf / peaks["bf16_tflops"],
-                    "traffic": None, "avg_launch_us": dur * 1e6, "share_of_step": round(sum(v) / iters / total, 4),
+                    "traffic": profiled_traffic("%s[%s]" % (name, tag)) if B == 1 else None,
+                    "avg_launch_us": dur * 1e6, "share_of_step": round(sum(v) / iters / total, 4),
                     "peak_source": peaks["src"], "algorithmic_flops": flops, "algorithmic_bytes": byts,
                     "note": "per-group MLP on %s; algorithmic FLOPs (the three tf32 partial products of the "
                             "fp32-grade split are counted once, so 1/6 of the bf16 peak is this design's ceiling); "
@@ -347,7 +361,7 @@ def run_ours(args, rank, world, local_rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--steps", type=int, default=1000)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--batch", type=int, default=1)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
