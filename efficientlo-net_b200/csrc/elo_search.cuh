@@ -190,4 +190,181 @@ __device__ __forceinline__ SearchCounts search_select_k(const float* __restrict_
     return c;
 }
 
+// ============================================================================================
+// Register-resident fast paths (kt <= 32 * S, S compile-time).  Same results as the functions above.
+// All S window cells of a lane are evaluated first -- their global loads are independent and in flight
+// together, one memory latency per query instead of one per 32 cells -- then the ballots / selection run
+// on registers.
+
+template <int S>
+__device__ __forceinline__ void eval_all(const float* __restrict__ g2, const int2* off, const Window& g, int ch,
+                                         int cw, float xc, float yc, float zc, bool (&val)[S], bool (&acc)[S],
+                                         unsigned (&key)[S], int (&hw)[S])
+{
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int i = 0; i < S; ++i) {
+        const int j = lane + 32 * i;
+        val[i] = false; acc[i] = false; key[i] = 0xffffffffu; hw[i] = 0;
+        if (j < g.kt) {
+            const Cand r = eval_candidate(g2, off[j], ch, cw, g, xc, yc, zc);
+            val[i] = r.valid; acc[i] = r.acc;
+            if (r.acc) { key[i] = __float_as_uint(r.d); hw[i] = pack_hw(r.hh, r.ww); }
+        }
+    }
+}
+
+template <int S, typename Emit>
+__device__ __forceinline__ SearchCounts search_random_k_fast(const float* __restrict__ g2, const int2* off,
+                                                             const Window& g, int ch, int cw, float xc, float yc,
+                                                             float zc, Emit emit)
+{
+    const int lane = threadIdx.x & 31;
+    const unsigned lt = (1u << lane) - 1u;
+    bool val[S], acc[S];
+    unsigned key[S];
+    int hw[S];
+    eval_all<S>(g2, off, g, ch, cw, xc, yc, zc, val, acc, key, hw);
+    SearchCounts c; c.nvalid = 0; c.nsel = 0; c.first = 0;
+#pragma unroll
+    for (int i = 0; i < S; ++i) {
+        if (32 * i >= g.kt) break;
+        const unsigned bv = __ballot_sync(FULL_MASK, val[i]);
+        const unsigned ba = __ballot_sync(FULL_MASK, acc[i]);
+        const int slot = c.nsel + __popc(ba & lt);
+        if (acc[i] && slot < g.K) emit(slot, hw[i] >> 16, hw[i] & 0xffff);
+        if (c.nsel == 0 && ba != 0u) c.first = __shfl_sync(FULL_MASK, hw[i], __ffs(ba) - 1);
+        const int na = __popc(ba);
+        if (c.nsel + na >= g.K) {
+            const int last = nth_set_bit(ba, g.K - c.nsel);
+            const unsigned upto = (last >= 31) ? FULL_MASK : ((2u << last) - 1u);
+            c.nvalid += __popc(bv & upto);
+            c.nsel = g.K;
+            return c;
+        }
+        c.nvalid += __popc(bv);
+        c.nsel += na;
+    }
+    return c;
+}
+
+// select-K on register keys.  Valid when K <= 32 and distance^2 < 1e10 (every accepted key is a real,
+// finite distance).  K rounds of "smallest (distance, scan position)"; this equals the reference's
+// swap-based selection sort whenever the K+1 smallest distances are pairwise different.  If two equal
+// distances meet among them, *tie is set and NOTHING has been emitted: the caller replays the exact
+// procedure (search_select_k) for this query.
+template <int S, typename Emit>
+__device__ __forceinline__ SearchCounts search_select_k_fast(const float* __restrict__ g2, const int2* off,
+                                                             const Window& g, int ch, int cw, float xc, float yc,
+                                                             float zc, int* nwritten, bool* tie, Emit emit)
+{
+    const int lane = threadIdx.x & 31;
+    bool val[S], acc[S];
+    unsigned key[S];
+    int hw[S];
+    eval_all<S>(g2, off, g, ch, cw, xc, yc, zc, val, acc, key, hw);
+    SearchCounts c; c.nvalid = 0; c.nsel = 0; c.first = 0;
+#pragma unroll
+    for (int i = 0; i < S; ++i) {
+        c.nvalid += __popc(__ballot_sync(FULL_MASK, val[i]));
+        c.nsel += __popc(__ballot_sync(FULL_MASK, acc[i]));
+    }
+    const int rounds = c.nsel < g.K ? c.nsel : g.K;
+    unsigned prev = 0u;
+    bool t = false;
+    int res = 0;
+    for (int s = 0; s < rounds; ++s) {
+        unsigned bd = key[0];
+        int bi = 0;
+#pragma unroll
+        for (int i = 1; i < S; ++i)
+            if (key[i] < bd) { bd = key[i]; bi = i; }
+        const unsigned md = __reduce_min_sync(FULL_MASK, bd);
+        const unsigned js = __reduce_min_sync(FULL_MASK, bd == md ? (unsigned)(bi * 32 + lane) : 0x7fffffffu);
+        t = t || (s > 0 && md == prev);
+        prev = md;
+        const int owner = js & 31, is = js >> 5;
+        int mine = hw[0];
+#pragma unroll
+        for (int i = 1; i < S; ++i)
+            if (i == is) mine = hw[i];
+        const int sel = __shfl_sync(FULL_MASK, mine, owner);
+        if (lane == s) res = sel;
+        if (lane == owner) {
+#pragma unroll
+            for (int i = 0; i < S; ++i)
+                if (i == is) key[i] = 0xffffffffu;
+        }
+    }
+    if (c.nsel > rounds && rounds > 0) {          // is the first cell left out as close as the last one taken?
+        unsigned bd = key[0];
+#pragma unroll
+        for (int i = 1; i < S; ++i) bd = min(bd, key[i]);
+        t = t || (__reduce_min_sync(FULL_MASK, bd) == prev);
+    }
+    *tie = t;
+    *nwritten = rounds;
+    c.first = __shfl_sync(FULL_MASK, res, 0);    // entry 0 after the first step (all-dummy array: cell (0,0))
+    if (!t && lane < rounds) emit(lane, res >> 16, res & 0xffff);
+    return c;
+}
+
+// kt -> smallest supported S with 32 * S >= kt (0: use the generic path)
+__host__ __device__ inline int fast_slots(int kt)
+{
+    const int s = (kt + 31) / 32;
+    if (s <= 1) return 1;
+    if (s <= 2) return 2;
+    if (s <= 3) return 3;
+    if (s <= 4) return 4;
+    if (s <= 6) return 6;
+    if (s <= 8) return 8;
+    if (s <= 12) return 12;
+    if (s <= 16) return 16;
+    return 0;
+}
+
+// One query, fast path when possible, exact replay on ties.  Returns counts; emit semantics as above.
+template <bool SELECT, typename Emit>
+__device__ __forceinline__ SearchCounts search_query(const float* __restrict__ g2, const int2* off, const Window& g,
+                                                     int ch, int cw, float xc, float yc, float zc, float* dist,
+                                                     int* hw, int* nwritten, bool fast_ok, Emit emit)
+{
+    const int S = fast_ok ? fast_slots(g.kt) : 0;
+    if (!SELECT) {
+        SearchCounts c;
+        switch (S) {
+            case 1: c = search_random_k_fast<1>(g2, off, g, ch, cw, xc, yc, zc, emit); break;
+            case 2: c = search_random_k_fast<2>(g2, off, g, ch, cw, xc, yc, zc, emit); break;
+            case 3: c = search_random_k_fast<3>(g2, off, g, ch, cw, xc, yc, zc, emit); break;
+            case 4: c = search_random_k_fast<4>(g2, off, g, ch, cw, xc, yc, zc, emit); break;
+            case 6: c = search_random_k_fast<6>(g2, off, g, ch, cw, xc, yc, zc, emit); break;
+            case 8: c = search_random_k_fast<8>(g2, off, g, ch, cw, xc, yc, zc, emit); break;
+            case 12: c = search_random_k_fast<12>(g2, off, g, ch, cw, xc, yc, zc, emit); break;
+            case 16: c = search_random_k_fast<16>(g2, off, g, ch, cw, xc, yc, zc, emit); break;
+            default: c = search_random_k(g2, off, g, ch, cw, xc, yc, zc, emit); break;
+        }
+        *nwritten = c.nsel;
+        return c;
+    }
+    bool tie = true;
+    SearchCounts c;
+    switch (S) {
+        case 1: c = search_select_k_fast<1>(g2, off, g, ch, cw, xc, yc, zc, nwritten, &tie, emit); break;
+        case 2: c = search_select_k_fast<2>(g2, off, g, ch, cw, xc, yc, zc, nwritten, &tie, emit); break;
+        case 3: c = search_select_k_fast<3>(g2, off, g, ch, cw, xc, yc, zc, nwritten, &tie, emit); break;
+        case 4: c = search_select_k_fast<4>(g2, off, g, ch, cw, xc, yc, zc, nwritten, &tie, emit); break;
+        case 6: c = search_select_k_fast<6>(g2, off, g, ch, cw, xc, yc, zc, nwritten, &tie, emit); break;
+        case 8: c = search_select_k_fast<8>(g2, off, g, ch, cw, xc, yc, zc, nwritten, &tie, emit); break;
+        case 12: c = search_select_k_fast<12>(g2, off, g, ch, cw, xc, yc, zc, nwritten, &tie, emit); break;
+        case 16: c = search_select_k_fast<16>(g2, off, g, ch, cw, xc, yc, zc, nwritten, &tie, emit); break;
+        default: break;
+    }
+    if (tie) {   // equal distances among the nearest (or no fast path): the reference's exact procedure
+        c = search_select_k(g2, off, g, ch, cw, xc, yc, zc, dist, hw, nwritten, emit);
+        __syncwarp();
+    }
+    return c;
+}
+
 }  // namespace elo

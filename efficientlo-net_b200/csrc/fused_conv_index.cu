@@ -35,6 +35,7 @@ struct IndexParams {
     float* out_vdis;   // (B, N, kt) or null
     float* out_mask;   // (B, N, K)
     long long total;   // B * N
+    bool fast_ok;      // register fast path allowed (K <= 32, distance^2 < 1e10)
 };
 
 __device__ __forceinline__ void fill_counts(float* row, int kt, int ones, int lane)
@@ -105,15 +106,8 @@ __global__ void __launch_bounds__(256) fused_conv_index_kernel(const IndexParams
             o_idx[slot * 3 + 2] = ww;
             o_mask[slot] = 1.0f;
         };
-        SearchCounts c;
         int filled;
-        if (SELECT) {
-            c = search_select_k(g2, off, g, ch, cw, xc, yc, zc, dist, hw, &filled, emit);
-            __syncwarp();
-        } else {
-            c = search_random_k(g2, off, g, ch, cw, xc, yc, zc, emit);
-            filled = c.nsel;
-        }
+        const SearchCounts c = search_query<SELECT>(g2, off, g, ch, cw, xc, yc, zc, dist, hw, &filled, p.fast_ok, emit);
         // select-K duplicates entry 0 even when nothing was in range (mask 1, index (b,0,0));
         // random-K only once a first neighbour was accepted (reference select :180-192, random :126-138)
         const bool copy = g.flag_copy == 1 && (SELECT || c.nsel > 0);
@@ -132,7 +126,7 @@ __global__ void __launch_bounds__(256) fused_conv_index_kernel(const IndexParams
 struct SearchSpec {
     QuerySet qs;
     Window g;
-    int select;
+    int select, fast_ok;
     long long total_q;        // batch * oh * ow
     int cta_begin;            // first CTA of this spec
     const float* xyz1;
@@ -175,12 +169,11 @@ __global__ void __launch_bounds__(256) multi_search_kernel(const __grid_constant
         if (fmaxf(sq3(xc, yc, zc), 1e-10f) <= 1e-10f) continue;
         const float* g2 = sp.xyz2 + (size_t)b * g.h2 * g.w2 * 3;
         auto emit = [&](int slot, int hh, int ww) { row[slot] = hh * g.w2 + ww; };
-        if (sp.select) {
-            int written;
-            search_select_k(g2, off, g, h / g.stride_h, w / g.stride_w, xc, yc, zc, dist, hw, &written, emit);
-        } else {
-            search_random_k(g2, off, g, h / g.stride_h, w / g.stride_w, xc, yc, zc, emit);
-        }
+        int written;
+        if (sp.select)
+            search_query<true>(g2, off, g, h / g.stride_h, w / g.stride_w, xc, yc, zc, dist, hw, &written, sp.fast_ok != 0, emit);
+        else
+            search_query<false>(g2, off, g, h / g.stride_h, w / g.stride_w, xc, yc, zc, dist, hw, &written, sp.fast_ok != 0, emit);
         __syncwarp();
     }
 }
@@ -219,6 +212,7 @@ static int launch_index(bool select, int B, int H, int W, int N, int kH, int kW,
     p.xyz1 = xyz1; p.xyz2 = xyz2; p.idx_n2 = idx_n2; p.random_hw = random_hw;
     p.out_idx = out_idx; p.out_valid = out_valid; p.out_vdis = out_vdis; p.out_mask = out_mask;
     p.total = (long long)B * N;
+    p.fast_ok = K <= 32 && p.g.d2max < 1e10f;
 
     int warps = 8;
     size_t smem = (size_t)kt * sizeof(int2);
@@ -284,6 +278,7 @@ extern "C" int elo_multi_search(const elo_search_desc* specs, int nspec, void* s
         sp.g.kt = (int)kt; sp.g.stride_h = w->stride_h; sp.g.stride_w = w->stride_w; sp.g.K = w->K;
         sp.g.flag_copy = 0; sp.g.d2max = w->distance * w->distance;
         sp.select = d->select ? 1 : 0;
+        sp.fast_ok = (w->K <= 32 && sp.g.d2max < 1e10f) ? 1 : 0;
         sp.total_q = (long long)d->batch_size * sp.qs.oh * sp.qs.ow;
         sp.xyz1 = d->xyz1; sp.xyz2 = d->xyz2; sp.random_hw = w->random_hw; sp.out_nbr = d->out_nbr;
         long long ctas = (sp.total_q + warps - 1) / warps;

@@ -251,3 +251,19 @@ def test_engine_graph_replay_is_deterministic(elo, world):
     assert torch.equal(q1, q2) and torch.equal(t1, t2)
     close(q1, world["out"][0], "engine q", atol=2e-5)
     close(t1, world["out"][1], "engine t", atol=2e-5)
+
+
+def test_forward_128x2048_matches_oracle(elo, cuda, mlp_engine):
+    """BASELINE.json configs[4] geometry: a dense 128x2048 scan (pyramid 32x256 / 16x128 / 8x64 / 8x32)."""
+    if mlp_engine == 0:
+        pytest.skip("one engine is enough for the geometry check")
+    H, W, N = 128, 2048, 300000
+    P = elo.params.init_params(1)
+    perms = elo.params.make_perms(1)
+    pc, T = elo.synth.synth_batch(1, H, W, N, seed0=7)
+    eye = torch.eye(4)[None]
+    want = go.get_model(pc, H, W, T, eye, eye, P, perms)
+    got = elo.get_model(pc.to(cuda), H, W, T.to(cuda), None, None, False, params=elo.ParamStore(P, cuda), perms=perms)
+    torch.cuda.synchronize()
+    for n, g, w in zip("l0_q l0_t l1_q l1_t l2_q l2_t l3_q l3_t l0_xyz_f1 q_gt t_gt".split(), got, want):
+        close(g, w, "128x2048 " + n, rtol=1e-4, atol=2e-5)
