@@ -27,6 +27,7 @@ struct ProjParams {
     float pi, az, vres, voff;
     unsigned* cellmin;
     float* out_xyz; float* out_feat; float* out_points;
+    int* out_cell;       // optional (B, N): cell of the point if it is (one of) the nearest of its cell, else -1
 };
 
 __device__ __forceinline__ float mul(float a, float b) { return __fmul_rn(a, b); }
@@ -146,7 +147,9 @@ __global__ void project_scatter_kernel(const ProjParams p)
         transform_point(p, b, n, x, y, z);
         const int cell = bin_point(p, x, y, z, r);
         const size_t gcell = (size_t)b * p.H * p.W + cell;
-        if (__float_as_uint(r) != p.cellmin[gcell]) continue;       // not the (a) nearest point of its cell
+        const bool winner = __float_as_uint(r) == p.cellmin[gcell];
+        if (slab == 0 && p.out_cell != nullptr) p.out_cell[pt] = winner ? cell : -1;
+        if (!winner) continue;                                       // not the (a) nearest point of its cell
         if (slab == 0) {
             // equal-range ties accumulate, like scatter_nd (model_util.py:271)
             if (x != 0.f) atomicAdd(p.out_xyz + gcell * 3 + 0, x);
@@ -188,6 +191,21 @@ __global__ void __launch_bounds__(POSE_THREADS) pose_head_kernel(const PoseParam
     __shared__ bool s_last;
     const int b = blockIdx.y, gidx = blockIdx.x;
     const int c = threadIdx.x & 63, sub = threadIdx.x >> 6;
+    // Head weights are constants: every CTA starts fetching its threads' share now (whichever CTA turns out to
+    // be the last one of the sample then runs the heads from registers, with no dependent global loads left).
+    float wbig[64], whead[8];
+    float bbig = 0.f, bhead = 0.f;
+    if (p.w_big != nullptr) {
+        const int o = threadIdx.x;
+#pragma unroll
+        for (int k = 0; k < 64; ++k) wbig[k] = __ldg(p.w_big + k * 256 + o);
+        bbig = __ldg(p.b_big + o);
+        const int hw_ = threadIdx.x >> 5, ln = threadIdx.x & 31;
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            whead[j] = hw_ < 4 ? __ldg(p.w_q + (ln + 32 * j) * 4 + hw_) : (hw_ < 7 ? __ldg(p.w_t + (ln + 32 * j) * 3 + (hw_ - 4)) : 0.f);
+        bhead = hw_ < 4 ? __ldg(p.b_q + hw_) : (hw_ < 7 ? __ldg(p.b_t + (hw_ - 4)) : 0.f);
+    }
 
     // online masked softmax over this CTA's slice of the points, per channel; the slice is short
     // (<= 4 * POSE_PT points) and all of a thread's loads are issued before any of them is used
@@ -283,21 +301,20 @@ __global__ void __launch_bounds__(POSE_THREADS) pose_head_kernel(const PoseParam
     __syncthreads();
     if (p.w_big == nullptr) return;     // softmax_valid only
     {   // conv1d 64 -> 256, no activation (pwclo_model.py:197); dropout is the identity at inference
-        const int o = threadIdx.x;
-        float acc = __ldg(p.b_big + o);
-#pragma unroll 16
-        for (int k = 0; k < 64; ++k) acc = fmaf(s_pool[k], __ldg(p.w_big + k * 256 + o), acc);
-        s_big[o] = acc;
+        float acc = bbig;
+#pragma unroll
+        for (int k = 0; k < 64; ++k) acc = fmaf(s_pool[k], wbig[k], acc);
+        s_big[threadIdx.x] = acc;
     }
     __syncthreads();
     {   // 7 heads of 256 MACs: warp w computes head w (q0..q3, t0..t2)
         const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
         if (warp < 7) {
             float acc = 0.f;
-            for (int k = lane; k < 256; k += 32)
-                acc = fmaf(s_big[k], warp < 4 ? __ldg(p.w_q + k * 4 + warp) : __ldg(p.w_t + k * 3 + (warp - 4)), acc);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc = fmaf(s_big[lane + 32 * j], whead[j], acc);
             for (int o = 16; o >= 1; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-            if (lane == 0) s_head[warp] = acc + (warp < 4 ? __ldg(p.b_q + warp) : __ldg(p.b_t + (warp - 4)));
+            if (lane == 0) s_head[warp] = acc + bhead;
         }
     }
     __syncthreads();
@@ -443,6 +460,7 @@ extern "C" int elo_project(const elo_project_desc* d, void* stream)
     p.pi = d->pi; p.az = d->az_res; p.vres = d->v_res; p.voff = d->v_off;
     p.cellmin = d->cellmin; p.out_xyz = d->out_xyz; p.out_feat = d->feat ? d->out_feat : nullptr;
     p.out_points = d->out_points;
+    p.out_cell = d->out_cell;
     cudaStream_t st = (cudaStream_t)stream;
     const int sms = device_info().sm_count;
     auto blocks = [&](long long work) {

@@ -87,7 +87,7 @@ def _scratch(name, shape, dtype, device, fill=None):
 
 
 def project_points(PC, Feature, H_input, W_input, mode=0, T=None, q=None, t=None, inner_batch=0,
-                   outer_stride=0, batch_size=None, want_points=False):
+                   outer_stride=0, batch_size=None, want_points=False, want_cells=False):
     """elo_project: optional PreProcess (mode 1) / pose warp (mode 2) fused with the spherical projection.
     PC may be any view whose last dimension is contiguous (e.g. point_cloud[:, :N, 0:3] of the
     (B, 2N, 6) input): it is read in place through its strides.  Returns (xyz (B,H,W,3),
@@ -117,7 +117,13 @@ def project_points(PC, Feature, H_input, W_input, mode=0, T=None, q=None, t=None
     if want_points:
         out_pts = torch.empty((B, N, 3), dtype=torch.float32, device=dev)
         d.out_points = out_pts.data_ptr()
+    out_cell = None
+    if want_cells:
+        out_cell = torch.empty((B, N), dtype=torch.int32, device=dev)
+        d.out_cell = out_cell.data_ptr()
     _lib.call("elo_project", d, dev)
+    if want_cells:
+        return out_xyz, out_feat, out_pts, out_cell
     return out_xyz, out_feat, out_pts
 
 

@@ -207,6 +207,8 @@ typedef struct {
     unsigned *cellmin;
     float *out_xyz, *out_feat;
     float *out_points;        /* optional (B, num_points, 3): the transformed points */
+    int *out_cell;            /* optional (B, num_points): cell (row*W+col) if the point is a nearest point of its
+                                 cell, else -1 -- lets a differentiable scatter be rebuilt on top (training) */
 } elo_project_desc;
 int elo_project(const elo_project_desc *desc, void *stream);
 
