@@ -23,7 +23,7 @@ struct ProjParams {
     int B, N, H, W, C, mode;
     const float* points; long long point_stride, batch_stride, outer_stride; int inner_batch;
     const float* feat;
-    const float* T; const float* q; const float* t;
+    const float* T; const int* T_apply; const float* q; const float* t;
     float pi, az, vres, voff;
     unsigned* cellmin;
     float* out_xyz; float* out_feat; float* out_points;
@@ -59,19 +59,22 @@ __device__ __forceinline__ void transform_point(const ProjParams& p, int b, int 
     x = __ldg(src); y = __ldg(src + 1); z = __ldg(src + 2);
     const bool valid = !(x == 0.f && y == 0.f && z == 0.f);
     if (p.mode == 1) {
-        // 35 m crop on the xy range, then the augmentation matrix on [p, 1] (identity at inference),
-        // then * valid (model_util.py:380-383, 390-417, 419-420)
+        // 35 m crop on the xy range, then the augmentation matrix on [p, 1] for the frame that is
+        // augmented (the other frame is NOT multiplied, not even by an identity), then * valid
+        // (model_util.py:380-383, 390-417, 419-420).  The final multiply keeps the sign of a zero
+        // coordinate (-0.0 * 0 = -0.0), which atan2 turns into azimuth pi instead of 0: kept as is.
         const float rxy = __fsqrt_rn(add(mul(x, x), mul(y, y)));
         float w = 1.f;
         if (rxy > 35.f) { x = 0.f; y = 0.f; z = 0.f; w = 0.f; }
-        if (p.T != nullptr) {
+        if (p.T != nullptr && (p.T_apply == nullptr || __ldg(p.T_apply + b) != 0)) {
             const float* T = p.T + (size_t)b * 16;
             const float nx = add(add(add(mul(T[0], x), mul(T[1], y)), mul(T[2], z)), mul(T[3], w));
             const float ny = add(add(add(mul(T[4], x), mul(T[5], y)), mul(T[6], z)), mul(T[7], w));
             const float nz = add(add(add(mul(T[8], x), mul(T[9], y)), mul(T[10], z)), mul(T[11], w));
             x = nx; y = ny; z = nz;
         }
-        if (!valid) { x = 0.f; y = 0.f; z = 0.f; }
+        const float m = valid ? 1.f : 0.f;
+        x = mul(x, m); y = mul(y, m); z = mul(z, m);
     } else if (p.mode == 2) {
         float q[4], qi[4], pq[4] = {0.f, x, y, z}, a[4], r[4];
         for (int i = 0; i < 4; ++i) q[i] = __ldg(p.q + (size_t)b * 4 + i);
@@ -456,7 +459,7 @@ extern "C" int elo_project(const elo_project_desc* d, void* stream)
     p.B = d->batch_size; p.N = d->num_points; p.H = d->H; p.W = d->W; p.C = d->feat ? d->C : 0; p.mode = d->mode;
     p.points = d->points; p.point_stride = d->point_stride; p.batch_stride = d->batch_stride;
     p.inner_batch = d->inner_batch; p.outer_stride = d->outer_stride;
-    p.feat = d->feat; p.T = d->T; p.q = d->q; p.t = d->t;
+    p.feat = d->feat; p.T = d->T; p.T_apply = d->T_apply; p.q = d->q; p.t = d->t;
     p.pi = d->pi; p.az = d->az_res; p.vres = d->v_res; p.voff = d->v_off;
     p.cellmin = d->cellmin; p.out_xyz = d->out_xyz; p.out_feat = d->feat ? d->out_feat : nullptr;
     p.out_points = d->out_points;

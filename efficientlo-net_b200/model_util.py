@@ -87,7 +87,7 @@ def _scratch(name, shape, dtype, device, fill=None):
 
 
 def project_points(PC, Feature, H_input, W_input, mode=0, T=None, q=None, t=None, inner_batch=0,
-                   outer_stride=0, batch_size=None, want_points=False, want_cells=False):
+                   outer_stride=0, batch_size=None, want_points=False, want_cells=False, T_apply=None):
     """elo_project: optional PreProcess (mode 1) / pose warp (mode 2) fused with the spherical projection.
     PC may be any view whose last dimension is contiguous (e.g. point_cloud[:, :N, 0:3] of the
     (B, 2N, 6) input): it is read in place through its strides.  Returns (xyz (B,H,W,3),
@@ -112,6 +112,9 @@ def project_points(PC, Feature, H_input, W_input, mode=0, T=None, q=None, t=None
         d.feat, d.out_feat = Feature.data_ptr(), out_feat.data_ptr()
     keep = [x.contiguous().float() if x is not None else None for x in (T, q, t)]
     d.T, d.q, d.t = (_lib.ptr(x) for x in keep)
+    if T_apply is not None:
+        T_apply = T_apply.to(device=dev, dtype=torch.int32).contiguous()
+        d.T_apply = T_apply.data_ptr()
     d.pi, d.az_res, d.v_res, d.v_off = projection_constants(H_input, W_input)
     d.cellmin, d.out_xyz = cellmin.data_ptr(), out_xyz.data_ptr()
     if want_points:
@@ -195,11 +198,18 @@ def gt_pose(T_gt, T_trans, T_trans_inv, aug_frame=None):
     return q, t
 
 
-def aug_matrices(T_trans, aug_frame, frame, B, device):
-    """Per-sample 4x4 applied to `frame` (1 or 2): T_trans where aug_frame == frame, identity elsewhere."""
-    af = torch.as_tensor(aug_frame).to(device)
-    eye = torch.eye(4, device=device).expand(B, 4, 4)
-    return torch.where((af == frame).view(B, 1, 1), T_trans.to(device).float(), eye).contiguous()
+def aug_setup(T_trans, aug_frame, B, device):
+    """Augmentation of model_util.py:386-417 for samples stacked frame-major (s = f*B + b): the matrices
+    (2B,4,4) and the flags (2B,) int32 saying which samples are multiplied -- only the frame named by
+    aug_frame[b] is; the other one is passed through untouched (no identity matmul: that would turn a
+    -0.0 coordinate into +0.0).  aug_frame None = frame 2 everywhere, built without a host copy."""
+    T = T_trans.to(device).float()
+    if aug_frame is None:
+        apply = torch.cat([torch.zeros(B, dtype=torch.int32, device=device), torch.ones(B, dtype=torch.int32, device=device)])
+    else:
+        af = torch.as_tensor(aug_frame).to(device)
+        apply = torch.cat([af == 1, af == 2]).to(torch.int32)
+    return torch.cat([T, T], 0).contiguous(), apply
 
 
 def PreProcess(PC_f1, PC_f2, T_gt, T_trans, T_trans_inv, aug_frame):
@@ -209,9 +219,10 @@ def PreProcess(PC_f1, PC_f2, T_gt, T_trans, T_trans_inv, aug_frame):
     B = PC_f1.shape[0]
     dev = PC_f1.device
     outs = []
-    for frame, pc in ((1, PC_f1), (2, PC_f2)):
-        T = aug_matrices(T_trans, aug_frame, frame, B, dev)
-        _, _, pts = project_points(pc, None, 2, 8, mode=1, T=T, want_points=True)
+    T2, apply = aug_setup(T_trans, aug_frame, B, dev)
+    for frame, pc in ((0, PC_f1), (1, PC_f2)):
+        _, _, pts = project_points(pc, None, 2, 8, mode=1, T=T2[:B], want_points=True,
+                                   T_apply=apply[frame * B:(frame + 1) * B])
         outs.append(pts)
     q_gt, t_gt = gt_pose(T_gt, T_trans, T_trans_inv, aug_frame)
     return outs[0], outs[1], q_gt, t_gt

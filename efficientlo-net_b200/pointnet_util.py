@@ -9,8 +9,10 @@ pwclo_model.py wires up the same way.  Each block is one or two fused sm_100a ke
     variable store made explicit;
   * the scan-order permutation each block draws with tf.random_shuffle (:45,104,193,270) can be passed
     in (``random_hw=``) so results are reproducible; if omitted it is drawn from torch's global RNG;
-  * only inference-mode batch norm (``is_training=False``) is implemented in this round -- training
-    mode raises NotImplementedError rather than silently using moving statistics.
+  * these fused blocks fold batch norm into the weights, i.e. serve ``is_training=False``; with
+    is_training=True they raise NotImplementedError rather than silently using moving statistics --
+    the training-mode graph (batch statistics + autograd) is train_graph.py, reached through
+    get_model(..., is_training=True).
 """
 import torch
 
@@ -73,10 +75,16 @@ def _window(kernel_size, K, distance, stride_h, stride_w, small_h, small_w, rand
     return w
 
 
+def _is_training(is_training):
+    return is_training is True or (isinstance(is_training, torch.Tensor) and bool(is_training))
+
+
 def _check_training(is_training):
-    if is_training is True or (isinstance(is_training, torch.Tensor) and bool(is_training)):
-        raise NotImplementedError("training-mode batch norm (batch statistics over B*N*K rows, "
-                                  "utils/tf_util.py:527) is not implemented; pass is_training=False")
+    if _is_training(is_training):
+        raise NotImplementedError("the fused kernels behind this block fold batch norm into the weights and so "
+                                  "only serve is_training=False; training-mode batch norm (batch statistics over "
+                                  "B*N*K rows, utils/tf_util.py:527) is provided for the whole graph by "
+                                  "get_model(..., is_training=True, params=TrainableParams) / train_graph.py")
 
 
 def _f32(t):

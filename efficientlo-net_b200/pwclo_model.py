@@ -62,7 +62,11 @@ def get_model(point_cloud, H_input, W_input, T_gt, T_trans, T_trans_inv, is_trai
     every run; ``aug_frame``: which frame each sample augments (the reference draws it with numpy at
     graph-build time, :59; default 2).  ``keep``: optional dict that receives named intermediates.
     Returns (l0_q, l0_t, l1_q, l1_t, l2_q, l2_t, l3_q, l3_t, l0_xyz_f1, q_gt, t_gt)."""
-    pu._check_training(is_training)
+    if pu._is_training(is_training):
+        # batch-statistics batch norm + autograd: the differentiable composition in train_graph.py
+        from . import train_graph
+        return train_graph.get_model(point_cloud, H_input, W_input, T_gt, T_trans, T_trans_inv, params,
+                                     bn_decay=bn_decay, perms=perms, aug_frame=aug_frame, keep=keep)
     store = params if isinstance(params, ParamStore) else (ParamStore(params, point_cloud.device) if params is not None
                                                            else current_store())
     if perms is None:
@@ -75,7 +79,6 @@ def get_model(point_cloud, H_input, W_input, T_gt, T_trans, T_trans_inv, is_trai
     oh, ow = pyramid_shapes(H_input, W_input)
     K = keep if keep is not None else {}
     want = keep is not None
-    aug_list = [2] * B if aug_frame is None else aug_frame
 
     with use_store(store):
         # ---- PreProcess (:61) + ProjectPC2SphericalRing x2 (:63-64), both frames in one pass.
@@ -84,13 +87,10 @@ def get_model(point_cloud, H_input, W_input, T_gt, T_trans, T_trans_inv, is_trai
         T_gt = T_gt.to(dev) if T_gt is not None else eye
         q_gt, t_gt = mu.gt_pose(T_gt, eye if T_trans is None else T_trans.to(dev),
                                 eye if T_trans_inv is None else T_trans_inv.to(dev), aug_frame)
-        T_aug = None
-        if not _all_identity(T_trans):
-            T_aug = torch.cat([mu.aug_matrices(T_trans, aug_list, 1, B, dev),
-                               mu.aug_matrices(T_trans, aug_list, 2, B, dev)], 0)
-        stride_pt, stride_b = point_cloud.stride(1), point_cloud.stride(0)
+        T_aug, T_apply = mu.aug_setup(eye if T_trans is None else T_trans, aug_frame, B, dev)
+        stride_pt = point_cloud.stride(1)
         xyz_in, _, _ = mu.project_points(point_cloud[:, :N, 0:3], None, H_input, W_input, mode=1, T=T_aug,
-                                         inner_batch=B, outer_stride=N * stride_pt, batch_size=2 * B)
+                                         T_apply=T_apply, inner_batch=B, outer_stride=N * stride_pt, batch_size=2 * B)
         if want:
             K["xyz_f1_proj"], K["xyz_f2_proj"] = xyz_in[:B], xyz_in[B:]
 
@@ -229,16 +229,6 @@ def get_model(point_cloud, H_input, W_input, T_gt, T_trans, T_trans_inv, is_trai
     l0_xyz_f1 = f1(xyz[0]).reshape(B, -1, 3)
     return (q_norm[0], t_lvl[0], q_norm[1], t_lvl[1], q_norm[2], t_lvl[2], q_norm[3], t_lvl[3], l0_xyz_f1,
             q_gt, t_gt)
-
-
-def _all_identity(T):
-    """Host-known identity augmentation (inference, main.py:311-312) lets the projection skip the matmul.
-    Only CPU tensors are inspected: a device tensor would need a sync, so it is treated as non-identity."""
-    if T is None:
-        return True
-    if T.is_cuda:
-        return False
-    return bool(torch.equal(T, torch.eye(4).expand_as(T)))
 
 
 def get_loss(l0_q, l0_t, l1_q, l1_t, l2_q, l2_t, l3_q, l3_t, q_gt, t_gt, w_x, w_q):

@@ -189,7 +189,8 @@ int elo_set_conv_small(const elo_group_mlp_desc *desc, void *stream);
 
 /* PreProcess / pose warp fused with ProjectPC2SphericalRing (model_util.py:181-292, 346-445;
  * pwclo_model.py:213-232).  mode 0: project the points as they are; mode 1: 35 m crop, optional
- * 4x4 augmentation T (B,4,4) (NULL = none), empty points stay empty; mode 2: p' = q p q^-1 + t with
+ * 4x4 augmentation T (B,4,4) (NULL = none) applied to the samples whose T_apply flag is set (NULL =
+ * all), then * valid as the reference does (signed zeros survive); mode 2: p' = q p q^-1 + t with
  * per-sample q (B,4) (w,x,y,z) and t (B,3), empty points stay empty.  Per cell the nearest point
  * wins (equal ranges accumulate); out_xyz (B,H,W,3), out_feat (B,H,W,C) are fully written.
  * points: sample b, point n at points + b*batch_stride + n*point_stride (floats) -- lets the kernel
@@ -207,6 +208,7 @@ typedef struct {
     unsigned *cellmin;
     float *out_xyz, *out_feat;
     float *out_points;        /* optional (B, num_points, 3): the transformed points */
+    const int *T_apply;       /* optional (B): mode 1 multiplies sample b by T[b] only if T_apply[b] != 0 */
     int *out_cell;            /* optional (B, num_points): cell (row*W+col) if the point is a nearest point of its
                                  cell, else -1 -- lets a differentiable scatter be rebuilt on top (training) */
 } elo_project_desc;

@@ -34,9 +34,43 @@ BN_EPS = 1e-3
 
 # ----------------------------------------------------------------------------------------------
 # primitives
+_TRAIN = []          # stack of dict(decay=..., moving={}) while a training-mode forward is being restated
+
+
+class training:
+    """with training(bn_decay) as moving: ...   conv2d then normalises with the statistics of the tensor
+    it is given (biased variance, tf_util.py:527 / FusedBatchNorm) and records the moving averages it
+    would assign (Bessel-corrected variance, moving -= (moving - batch) * (1 - decay)) in `moving`;
+    P itself is left untouched.  Dropout is NOT restated (random); compare with dropout disabled."""
+
+    def __init__(self, bn_decay=None):
+        self.state = dict(decay=0.9 if bn_decay is None else float(bn_decay), moving={})
+
+    def __enter__(self):
+        _TRAIN.append(self.state)
+        return self.state["moving"]
+
+    def __exit__(self, *a):
+        _TRAIN.pop()
+
+
 def conv2d(x, P, scope, relu=True, bn=True):
-    """1x1 conv + bias + inference batch-norm + ReLU on the last axis (tf_util.py:120-185)."""
+    """1x1 conv + bias + batch-norm + ReLU on the last axis (tf_util.py:120-185); inference statistics
+    unless inside a `training` block."""
     y = x @ P[scope + "/weights"].to(x.dtype) + P[scope + "/biases"].to(x.dtype)
+    if bn and _TRAIN:
+        st = _TRAIN[-1]
+        flat = y.reshape(-1, y.shape[-1])
+        n = flat.shape[0]
+        mean = flat.mean(0)
+        var = ((flat - mean) ** 2).mean(0)
+        mv = st["moving"]
+        mm0 = mv.get(scope + "/bn/moving_mean", P[scope + "/bn/moving_mean"]).to(x.dtype)
+        mv0 = mv.get(scope + "/bn/moving_variance", P[scope + "/bn/moving_variance"]).to(x.dtype)
+        mv[scope + "/bn/moving_mean"] = (mm0 - (mm0 - mean) * (1 - st["decay"])).detach()
+        mv[scope + "/bn/moving_variance"] = (mv0 - (mv0 - var * (n / max(n - 1, 1))) * (1 - st["decay"])).detach()
+        y = (y - mean) / torch.sqrt(var + BN_EPS) * P[scope + "/bn/gamma"].to(x.dtype) + P[scope + "/bn/beta"].to(x.dtype)
+        return torch.relu(y) if relu else y
     if bn:
         mean = P[scope + "/bn/moving_mean"].to(x.dtype)
         var = P[scope + "/bn/moving_variance"].to(x.dtype)
@@ -72,7 +106,7 @@ def fused_conv(mode, xyz1, xyz2, idx_n2, random_hw, kH, kW, K, distance, stride_
     """The custom op through the pinned C restatement; returns (idx int64 (B,n,K,3), mask (B,n,K,1))."""
     B, H, W, _ = xyz1.shape
     n = idx_n2.shape[1]
-    sel, _, _, mask = io.port(mode, xyz1.float().numpy(), xyz2.float().numpy(), idx_n2.numpy(),
+    sel, _, _, mask = io.port(mode, xyz1.detach().float().numpy(), xyz2.detach().float().numpy(), idx_n2.numpy(),
                               np.asarray(random_hw, dtype=np.int32), H, W, n, kH, kW, K, flag_copy,
                               float(distance), stride_h, stride_w, nthreads=8)
     return torch.from_numpy(sel).long(), torch.from_numpy(mask).to(xyz1.dtype)

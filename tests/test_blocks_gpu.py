@@ -61,17 +61,23 @@ def test_input_projection_and_preprocess(elo, world):
                                                   outer_stride=NPTS * 6, batch_size=4)
     torch.cuda.synchronize()
     want = torch.cat([world["keep"]["xyz_f1_proj"], world["keep"]["xyz_f2_proj"]], 0)
-    # bins are integers: the images must agree exactly except where atan2f/asinf of the two libms differ
-    # in the last bit right on a bin edge (allow a handful of the 460 800 cells)
+    # bins are integers: the images must agree exactly -- including the cells at azimuth +-pi that receive the
+    # empty points whose x is -0.0 (the synthetic scans contain them; model_util.py:419 keeps the sign)
+    # The only tolerated difference: a point whose azimuth / elevation lies on a bin edge to the last bit, where
+    # CUDA's atan2f / asinf and the host libm may round differently and the point moves to the ADJACENT cell.
     diff = (xyz.cpu() != want).any(-1)
-    assert int(diff.sum()) <= 8, "%d cells differ" % int(diff.sum())
+    cells = diff.nonzero().tolist()
+    assert len(cells) <= 4, "%d cells differ: %s" % (len(cells), cells[:8])
+    for b, h, w in cells:
+        assert any(c[0] == b and abs(c[1] - h) + abs(c[2] - w) == 1 for c in cells), "isolated differing cell %s" % [b, h, w]
+    assert bool((world["pc"][:, :NPTS, 0] == 0).logical_and(torch.signbit(world["pc"][:, :NPTS, 0])).any())
     assert int((want != 0).any(-1).sum()) > 300000
     # plain ProjectPC2SphericalRing on the same points, API of model_util.py:181
     f1 = pc[:, :NPTS, 0:3].contiguous()
     xyz_plain, again = elo.ProjectPC2SphericalRing(f1, None, H_IN, W_IN)
     want_plain, _ = go.ProjectPC2SphericalRing(world["pc"][:, :NPTS, 0:3], None, H_IN, W_IN)
     assert again is xyz_plain
-    assert int((xyz_plain.cpu() != want_plain).any(-1).sum()) <= 8
+    assert int((xyz_plain.cpu() != want_plain).any(-1).sum()) <= 4
 
 
 @pytest.mark.parametrize("lvl", [2, 1, 0])
