@@ -304,6 +304,10 @@ def run_ours(args, rank, world, local_rank):
         total = sum(sum(v) for v in agg.values()) / iters
         top = sorted(agg.items(), key=lambda kv: -sum(kv[1]))
         shares = {"%s[%s]" % k: round(sum(v) / iters / total, 4) for k, v in top[:8]}
+        if args.kernel_times:
+            for (name, tag), v in sorted(agg.items(), key=lambda kv: kv[0][1] + kv[0][0]):
+                sys.stderr.write("%-28s %-6s n=%d  %8.2f us/launch\n" % (name, tag, len(v) // iters, sum(v) / len(v) * 1e3))
+            sys.stderr.write("sum of kernel times per forward (un-graphed, event-timed): %.1f us\n" % (total * 1e3))
         peaks = measured_peaks()
         engine = "tcgen05 tf32x3" if elo._lib.mlp_engine() == 1 else "fp32 FFMA"
         for (name, tag), v in top:
@@ -344,7 +348,8 @@ def run_ours(args, rank, world, local_rank):
                            "l2": "inputs rotate over %d distinct batches (%.0f MB > 126 MB L2); weights stay resident"
                                  % (pool, pool * batch_bytes / 1e6),
                            "graph": "kernel-by-kernel launches (--no-graph)" if args.no_graph else
-                                    "whole forward captured as one CUDA graph"},
+                                    "whole forward captured as one CUDA graph",
+                           "pdl": bool(elo._lib.lib().elo_get_pdl())},
                 "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": "frame-pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": e2e_ms / args.steps, "api": "PWCLOPipeline.run (pinned host batches in, (q,t) out; "
@@ -368,6 +373,7 @@ def main():
     ap.add_argument("--cpu-pairs", type=int, default=6)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--engine", default="tc", choices=["tc", "ffma"], help="MLP engine: tcgen05 3xTF32 or fp32 FFMA")
+    ap.add_argument("--kernel-times", action="store_true", help="print every kernel's average time to stderr")
     ap.add_argument("--no-graph", action="store_true", help="launch kernel by kernel (for ncu launch lists)")
     ap.add_argument("--pool", type=int, default=0, help="input batches to rotate (0 = enough to exceed L2)")
     args = ap.parse_args()

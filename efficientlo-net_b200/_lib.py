@@ -116,6 +116,10 @@ def lib():
         handle.elo_set_mlp_engine.restype = _c_int
         handle.elo_get_mlp_engine.argtypes = []
         handle.elo_get_mlp_engine.restype = _c_int
+        handle.elo_set_pdl.argtypes = [_c_int]
+        handle.elo_set_pdl.restype = _c_int
+        handle.elo_get_pdl.argtypes = []
+        handle.elo_get_pdl.restype = _c_int
         for name, argtypes in SIGNATURES.items():
             fn = getattr(handle, name)
             fn.argtypes = argtypes
@@ -156,6 +160,11 @@ def mlp_engine():
 
 def set_mlp_engine(engine):
     check(lib().elo_set_mlp_engine(int(engine)), "elo_set_mlp_engine")
+
+
+def set_pdl(on):
+    """Programmatic dependent launch between this library's kernels (default on)."""
+    check(lib().elo_set_pdl(int(bool(on))), "elo_set_pdl")
 
 
 def launch_count():

@@ -38,6 +38,7 @@ struct TcPipe {
     uint64_t* done;
     uint32_t nring;
     uint32_t tbase;       // TMEM base address
+    uint32_t* tmem_holder;    // shared-memory word tcgen05.alloc writes the base address to
     uint32_t layer;       // layers completed so far (parity of a_ready / done)
     uint32_t chunk;       // chunks consumed so far (MMA warp)
     uint32_t cslot, cround;   // ring slot / lap of the next chunk (MMA warp)
@@ -55,27 +56,45 @@ struct TcPipe {
     }
 
     // all threads; bars must hold 2 * MAX_RING + 2 mbarriers; contains __syncthreads
-    __device__ __forceinline__ void init(float* ring_, uint64_t* bars, uint32_t nring_, uint32_t* tmem_holder,
-                                         const float* bias_gmem, float* bias_smem, int nbias, long long* tlog_ = nullptr)
+    // Set-up, split in two so that a kernel can put its first loads of upstream data between the halves:
+    //   begin(): per-role work on constants only -- the TMA warp initialises the mbarriers, the MMA warp copies
+    //            the biases to shared memory, warp 0 allocates tensor memory;
+    //   join():  CTA-wide barrier that publishes all of it.
+    // Under programmatic dependent launch begin() runs while the previous kernel is still finishing; the compute
+    // warps call pdl_wait() after it, the other two warps never touch upstream data and do not wait at all.
+    __device__ __forceinline__ void begin(float* ring_, uint64_t* bars, uint32_t nring_, uint32_t* tmem_holder_,
+                                          const float* bias_gmem, float* bias_smem, int nbias, long long* tlog_ = nullptr)
     {
         tlog = tlog_;
         stamp(0);
         ring = ring_; full = bars; empty = bars + MAX_RING; a_ready = bars + 2 * MAX_RING; done = a_ready + 1;
         nring = nring_; layer = 0; chunk = 0; cslot = 0; cround = 0; bias = bias_smem;
-        // every epilogue needs its biases at once: one L2 round trip here instead of one per layer
-        for (int i = threadIdx.x; i < nbias; i += blockDim.x) bias_smem[i] = __ldg(bias_gmem + i);
-        if (threadIdx.x == 0) {
+        tmem_holder = tmem_holder_;
+        const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        if (warp == COMPUTE_WARPS && lane == 0) {
             for (uint32_t i = 0; i < nring; ++i) { mbar_init(full + i, 1); mbar_init(empty + i, 1); }
             mbar_init(a_ready, COMPUTE_WARPS);
             mbar_init(done, 1);
             mbar_fence_init();
         }
-        if ((threadIdx.x >> 5) == 0) tc::tmem_alloc(tmem_holder, tc::TMEM_COLS);
+        // every epilogue needs its biases at once: one L2 round trip here instead of one per layer
+        if (warp == COMPUTE_WARPS + 1)
+            for (int i = lane; i < nbias; i += 32) bias_smem[i] = __ldg(bias_gmem + i);
+        if (warp == 0) tc::tmem_alloc(tmem_holder, tc::TMEM_COLS);
+    }
+    __device__ __forceinline__ void join()
+    {
         tc::fence_before_sync();
         __syncthreads();
         tc::fence_after_sync();
         tbase = *tmem_holder;
         stamp(1);
+    }
+    __device__ __forceinline__ void init(float* ring_, uint64_t* bars, uint32_t nring_, uint32_t* tmem_holder_,
+                                         const float* bias_gmem, float* bias_smem, int nbias, long long* tlog_ = nullptr)
+    {
+        begin(ring_, bars, nring_, tmem_holder_, bias_gmem, bias_smem, nbias, tlog_);
+        join();
     }
     // after the last epilogue: compute warps only
     __device__ __forceinline__ void finish()

@@ -47,6 +47,8 @@ __global__ void __launch_bounds__(LAUNCH_THREADS, 1) group_mlp_max_kernel(const 
 {
     constexpr int RS = NB * 64;
     extern __shared__ __align__(128) unsigned char smem_raw[];
+    pdl_trigger();
+    pdl_wait();          // cross-check engine: no prologue overlap, plain stream order from here
     SmemCarver sc(smem_raw);
     float* ring = sc.take<float>((size_t)p.nring * CHUNK_FLOATS);
     uint64_t* bars = sc.take<uint64_t>(2 * MAX_RING);
@@ -189,6 +191,8 @@ __global__ void __launch_bounds__(LAUNCH_THREADS, 1) cost_volume_1_kernel(const 
 {
     constexpr int RS = NB * 64;
     extern __shared__ __align__(128) unsigned char smem_raw[];
+    pdl_trigger();
+    pdl_wait();          // cross-check engine: no prologue overlap, plain stream order from here
     SmemCarver sc(smem_raw);
     float* ring = sc.take<float>((size_t)p.nring * CHUNK_FLOATS);
     uint64_t* bars = sc.take<uint64_t>(2 * MAX_RING);
@@ -293,6 +297,8 @@ __global__ void __launch_bounds__(LAUNCH_THREADS, 1) cost_volume_2_kernel(const 
 {
     constexpr int RS = NB * 64;
     extern __shared__ __align__(128) unsigned char smem_raw[];
+    pdl_trigger();
+    pdl_wait();          // cross-check engine: no prologue overlap, plain stream order from here
     SmemCarver sc(smem_raw);
     float* ring = sc.take<float>((size_t)p.nring * CHUNK_FLOATS);
     uint64_t* bars = sc.take<uint64_t>(2 * MAX_RING);
@@ -406,6 +412,8 @@ __global__ void __launch_bounds__(LAUNCH_THREADS, 1) row_mlp_kernel(const RowMlp
 {
     constexpr int RS = NB * 64;
     extern __shared__ __align__(128) unsigned char smem_raw[];
+    pdl_trigger();
+    pdl_wait();          // cross-check engine: no prologue overlap, plain stream order from here
     SmemCarver sc(smem_raw);
     float* ring = sc.take<float>((size_t)p.nring * CHUNK_FLOATS);
     uint64_t* bars = sc.take<uint64_t>(2 * MAX_RING);
@@ -603,14 +611,19 @@ __global__ void __launch_bounds__(TC_LAUNCH_THREADS, 1) group_mlp_max_tc_kernel(
     const long long q0 = p.q_base[set] + (long long)blockIdx.x * p.qt;
     const long long total_q = p.q_end[set];
     const int cells2 = g.h2 * g.w2;
-    // neighbour table first: its global loads overlap the barrier / TMEM set-up below
-    if (warp < COMPUTE_WARPS && p.nbr_in[set] != nullptr)
-        tc_load_nbr(p.qs, rows, p.xyz1, p.nbr_in[set], q0, p.qt, total_q, nbr, ctr);
+    // Prologue on constants only (barriers, tensor memory, biases; the producer warp starts streaming weights):
+    // under programmatic dependent launch it runs while the kernel before this one is still finishing.
+    pdl_trigger();
     TcPipe pipe;
     int nbias = 0;
     for (int l = 0; l < p.nl; ++l) nbias += p.cout[l];
-    pipe.init(sm.ring, sm.bars, p.nring, sm.tmem_holder, p.weights[set] + (size_t)p.total_chunks * TC_CHUNK_FLOATS,
-              sm.bias, nbias, p.tlog);
+    pipe.begin(sm.ring, sm.bars, p.nring, sm.tmem_holder, p.weights[set] + (size_t)p.total_chunks * TC_CHUNK_FLOATS,
+               sm.bias, nbias, p.tlog);
+    if (warp < COMPUTE_WARPS) {
+        pdl_wait();                              // from here on: data written by earlier kernels
+        if (p.nbr_in[set] != nullptr) tc_load_nbr(p.qs, rows, p.xyz1, p.nbr_in[set], q0, p.qt, total_q, nbr, ctr);
+    }
+    pipe.join();
     if (warp == COMPUTE_WARPS) { pipe.produce(p.weights[set], p.total_chunks); return; }
     if (warp == COMPUTE_WARPS + 1) {
         if (tc::elect_one()) {
@@ -695,10 +708,15 @@ __global__ void __launch_bounds__(TC_LAUNCH_THREADS, 1) cost_volume_1_tc_kernel(
     int* nbr = sm.nbr; float* ctr = sm.ctr; float* X = sm.X;
     const long long q0 = (long long)blockIdx.x * p.qt;
     const int cells = g.h2 * g.w2;
-    if (warp < COMPUTE_WARPS) tc_load_nbr(p.qs, rows, p.xyz1, p.nbr_in, q0, p.qt, p.total_q, nbr, ctr);
+    pdl_trigger();
     TcPipe pipe;
-    pipe.init(sm.ring, sm.bars, p.nring, sm.tmem_holder, p.weights + (size_t)p.total_chunks * TC_CHUNK_FLOATS,
-              sm.bias, 128 + 64 + 64 + 64 + 128 + 64, p.tlog);
+    pipe.begin(sm.ring, sm.bars, p.nring, sm.tmem_holder, p.weights + (size_t)p.total_chunks * TC_CHUNK_FLOATS,
+               sm.bias, 128 + 64 + 64 + 64 + 128 + 64, p.tlog);
+    if (warp < COMPUTE_WARPS) {
+        pdl_wait();
+        tc_load_nbr(p.qs, rows, p.xyz1, p.nbr_in, q0, p.qt, p.total_q, nbr, ctr);
+    }
+    pipe.join();
     if (warp == COMPUTE_WARPS) { pipe.produce(p.weights, p.total_chunks); return; }
     if (warp == COMPUTE_WARPS + 1) {
         if (tc::elect_one()) {
@@ -804,10 +822,15 @@ __global__ void __launch_bounds__(TC_LAUNCH_THREADS, 1) cost_volume_2_tc_kernel(
     int* nbr = sm.nbr; float* ctr = sm.ctr; float* X = sm.X;
     const long long q0 = (long long)blockIdx.x * p.qt;
     const int cells = g.h2 * g.w2;
-    if (warp < COMPUTE_WARPS) tc_load_nbr(p.qs, rows, p.xyz1, p.nbr_in, q0, p.qt, p.total_q, nbr, ctr);
+    pdl_trigger();
     TcPipe pipe;
-    pipe.init(sm.ring, sm.bars, p.nring, sm.tmem_holder, p.weights + (size_t)p.total_chunks * TC_CHUNK_FLOATS,
-              sm.bias, 64 + 128 + 64, p.tlog);
+    pipe.begin(sm.ring, sm.bars, p.nring, sm.tmem_holder, p.weights + (size_t)p.total_chunks * TC_CHUNK_FLOATS,
+               sm.bias, 64 + 128 + 64, p.tlog);
+    if (warp < COMPUTE_WARPS) {
+        pdl_wait();
+        tc_load_nbr(p.qs, rows, p.xyz1, p.nbr_in, q0, p.qt, p.total_q, nbr, ctr);
+    }
+    pipe.join();
     if (warp == COMPUTE_WARPS) { pipe.produce(p.weights, p.total_chunks); return; }
     if (warp == COMPUTE_WARPS + 1) {
         if (tc::elect_one()) {
@@ -876,6 +899,7 @@ __global__ void __launch_bounds__(TC_LAUNCH_THREADS, 1) row_mlp_tc_kernel(const 
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int set = blockIdx.y, warp = threadIdx.x >> 5;
     TcSmem sm = tc_carve(smem_raw, p.nring, 0, (size_t)p.stage_ch * RS);
+    pdl_trigger();
     TcPipe pipe;
     int nbias = 0;
     for (int ph = 0; ph < p.nphase; ++ph)
@@ -892,6 +916,7 @@ __global__ void __launch_bounds__(TC_LAUNCH_THREADS, 1) row_mlp_tc_kernel(const 
             }
         return;
     }
+    pdl_wait();
     float* X = sm.X;
     const long long r0 = (long long)blockIdx.x * p.rt;
     const long long rows = p.rows;
@@ -1081,9 +1106,7 @@ static int launch_tc(Kernel kern, const Params& p, dim3 grid, size_t bytes, cuda
 {
     int rc = set_smem(kern, bytes, what);
     if (rc) return rc;
-    kern<<<grid, TC_LAUNCH_THREADS, bytes, st>>>(p);
-    count_launches(1);
-    cudaError_t err = cudaGetLastError();
+    cudaError_t err = launch(kern, grid, dim3(TC_LAUNCH_THREADS), bytes, st, p);
     return err == cudaSuccess ? ELO_OK : set_cuda_error(err, what);
 }
 
@@ -1166,15 +1189,14 @@ extern "C" int elo_group_mlp_max(const elo_group_mlp_desc* d, void* stream)
     p.nring = pick_ring(smem(tc.nb), p.total_chunks);
     const size_t bytes = smem(tc.nb) + (size_t)p.nring * CHUNK_BYTES;
     cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t err;
     if (tc.nb == 1) {
         if ((rc = set_smem(group_mlp_max_kernel<1>, bytes, "group_mlp_max smem"))) return rc;
-        group_mlp_max_kernel<1><<<grid, LAUNCH_THREADS, bytes, st>>>(p);
+        err = launch(group_mlp_max_kernel<1>, dim3(grid), dim3(LAUNCH_THREADS), bytes, st, p);
     } else {
         if ((rc = set_smem(group_mlp_max_kernel<2>, bytes, "group_mlp_max smem"))) return rc;
-        group_mlp_max_kernel<2><<<grid, LAUNCH_THREADS, bytes, st>>>(p);
+        err = launch(group_mlp_max_kernel<2>, dim3(grid), dim3(LAUNCH_THREADS), bytes, st, p);
     }
-    count_launches(1);
-    cudaError_t err = cudaGetLastError();
     return err == cudaSuccess ? ELO_OK : set_cuda_error(err, "group_mlp_max launch");
 }
 
@@ -1225,15 +1247,14 @@ extern "C" int elo_cost_volume_1(const elo_cost_volume_desc* d, void* stream)
     p.nring = pick_ring(smem(tc.nb), p.total_chunks);
     const size_t bytes = smem(tc.nb) + (size_t)p.nring * CHUNK_BYTES;
     cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t err;
     if (tc.nb == 1) {
         if ((rc = set_smem(cost_volume_1_kernel<1>, bytes, "cost_volume_1 smem"))) return rc;
-        cost_volume_1_kernel<1><<<tc.tiles, LAUNCH_THREADS, bytes, st>>>(p);
+        err = launch(cost_volume_1_kernel<1>, dim3(tc.tiles), dim3(LAUNCH_THREADS), bytes, st, p);
     } else {
         if ((rc = set_smem(cost_volume_1_kernel<2>, bytes, "cost_volume_1 smem"))) return rc;
-        cost_volume_1_kernel<2><<<tc.tiles, LAUNCH_THREADS, bytes, st>>>(p);
+        err = launch(cost_volume_1_kernel<2>, dim3(tc.tiles), dim3(LAUNCH_THREADS), bytes, st, p);
     }
-    count_launches(1);
-    cudaError_t err = cudaGetLastError();
     return err == cudaSuccess ? ELO_OK : set_cuda_error(err, "cost_volume_1 launch");
 }
 
@@ -1277,15 +1298,14 @@ extern "C" int elo_cost_volume_2(const elo_cost_volume_desc* d, void* stream)
     p.nring = pick_ring(smem(tc.nb), p.total_chunks);
     const size_t bytes = smem(tc.nb) + (size_t)p.nring * CHUNK_BYTES;
     cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t err;
     if (tc.nb == 1) {
         if ((rc = set_smem(cost_volume_2_kernel<1>, bytes, "cost_volume_2 smem"))) return rc;
-        cost_volume_2_kernel<1><<<tc.tiles, LAUNCH_THREADS, bytes, st>>>(p);
+        err = launch(cost_volume_2_kernel<1>, dim3(tc.tiles), dim3(LAUNCH_THREADS), bytes, st, p);
     } else {
         if ((rc = set_smem(cost_volume_2_kernel<2>, bytes, "cost_volume_2 smem"))) return rc;
-        cost_volume_2_kernel<2><<<tc.tiles, LAUNCH_THREADS, bytes, st>>>(p);
+        err = launch(cost_volume_2_kernel<2>, dim3(tc.tiles), dim3(LAUNCH_THREADS), bytes, st, p);
     }
-    count_launches(1);
-    cudaError_t err = cudaGetLastError();
     return err == cudaSuccess ? ELO_OK : set_cuda_error(err, "cost_volume_2 launch");
 }
 
@@ -1377,14 +1397,13 @@ extern "C" int elo_row_mlp(const elo_row_mlp_desc* d, void* stream)
     const size_t bytes = smem(tc.nb) + (size_t)p.nring * CHUNK_BYTES;
     cudaStream_t st = (cudaStream_t)stream;
     int rc;
+    cudaError_t err;
     if (tc.nb == 1) {
         if ((rc = set_smem(row_mlp_kernel<1>, bytes, "row_mlp smem"))) return rc;
-        row_mlp_kernel<1><<<grid, LAUNCH_THREADS, bytes, st>>>(p);
+        err = launch(row_mlp_kernel<1>, dim3(grid), dim3(LAUNCH_THREADS), bytes, st, p);
     } else {
         if ((rc = set_smem(row_mlp_kernel<2>, bytes, "row_mlp smem"))) return rc;
-        row_mlp_kernel<2><<<grid, LAUNCH_THREADS, bytes, st>>>(p);
+        err = launch(row_mlp_kernel<2>, dim3(grid), dim3(LAUNCH_THREADS), bytes, st, p);
     }
-    count_launches(1);
-    cudaError_t err = cudaGetLastError();
     return err == cudaSuccess ? ELO_OK : set_cuda_error(err, "row_mlp launch");
 }

@@ -61,6 +61,8 @@ template <bool SELECT>
 __global__ void __launch_bounds__(256) fused_conv_index_kernel(const IndexParams p)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    pdl_trigger();
+    pdl_wait();
     const Window g = p.g;
     int2* off = reinterpret_cast<int2*>(smem_raw);
     const int nwarps = blockDim.x >> 5;
@@ -143,6 +145,8 @@ struct MultiSearchParams {
 __global__ void __launch_bounds__(256) multi_search_kernel(const __grid_constant__ MultiSearchParams p)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    pdl_trigger();
+    pdl_wait();          // the grids (and, in eager calls, the scan orders) come from the kernels before
     int si = 0;
     while (si + 1 < p.nspec && (int)blockIdx.x >= p.spec[si + 1].cta_begin) ++si;
     const SearchSpec& sp = p.spec[si];
@@ -234,12 +238,10 @@ static int launch_index(bool select, int B, int H, int W, int N, int kH, int kW,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (err != cudaSuccess) return set_cuda_error(err, "cudaFuncSetAttribute(select_k)");
         }
-        fused_conv_index_kernel<true><<<(unsigned)ctas, warps * 32, smem, stream>>>(p);
+        err = launch(fused_conv_index_kernel<true>, dim3((unsigned)ctas), dim3(warps * 32), smem, stream, p);
     } else {
-        fused_conv_index_kernel<false><<<(unsigned)ctas, warps * 32, smem, stream>>>(p);
+        err = launch(fused_conv_index_kernel<false>, dim3((unsigned)ctas), dim3(warps * 32), smem, stream, p);
     }
-    count_launches(1);
-    err = cudaGetLastError();
     if (err != cudaSuccess) return set_cuda_error(err, select ? "fused_conv_select_k launch" : "fused_conv_random_k launch");
     return ELO_OK;
 }
@@ -296,9 +298,7 @@ extern "C" int elo_multi_search(const elo_search_desc* specs, int nspec, void* s
         err = cudaFuncSetAttribute(multi_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (err != cudaSuccess) return set_cuda_error(err, "cudaFuncSetAttribute(multi_search)");
     }
-    multi_search_kernel<<<(unsigned)ctas_total, warps * 32, smem, (cudaStream_t)stream>>>(p);
-    count_launches(1);
-    err = cudaGetLastError();
+    err = launch(multi_search_kernel, dim3((unsigned)ctas_total), dim3(warps * 32), smem, (cudaStream_t)stream, p);
     return err == cudaSuccess ? ELO_OK : set_cuda_error(err, "multi_search launch");
 }
 

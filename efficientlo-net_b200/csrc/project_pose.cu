@@ -12,6 +12,8 @@
 // a bin or a range winner is therefore written with explicit round-to-nearest intrinsics in the
 // reference's operation order, which makes the integer outcomes (cells, winners) reproducible.
 #include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdlib.h>
 #include <math.h>
 
 #include "../../include/elo_b200.h"
@@ -104,6 +106,8 @@ __device__ __forceinline__ int bin_point(const ProjParams& p, float x, float y, 
 
 __global__ void project_init_kernel(const ProjParams p)
 {
+    pdl_trigger();
+    pdl_wait();          // the output images may alias memory an earlier kernel is still reading
     const long long cells = (long long)p.B * p.H * p.W;
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long stride = (long long)gridDim.x * blockDim.x;
@@ -115,6 +119,8 @@ __global__ void project_init_kernel(const ProjParams p)
 
 __global__ void project_bin_kernel(const ProjParams p)
 {
+    pdl_trigger();
+    pdl_wait();
     const long long total = (long long)p.B * p.N;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
          i += (long long)gridDim.x * blockDim.x) {
@@ -139,6 +145,8 @@ __global__ void project_bin_kernel(const ProjParams p)
 // one thread per (point, 4-channel slab): slab 0 carries xyz, slabs 1.. the features
 __global__ void project_scatter_kernel(const ProjParams p)
 {
+    pdl_trigger();
+    pdl_wait();
     const int slabs = 1 + (p.out_feat != nullptr ? (p.C + 3) / 4 : 0);
     const long long total = (long long)p.B * p.N * slabs;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
@@ -189,6 +197,7 @@ constexpr int POSE_PT = 8;          // points per thread; a CTA covers 4 * POSE_
 
 __global__ void __launch_bounds__(POSE_THREADS) pose_head_kernel(const PoseParams p)
 {
+    pdl_trigger();
     __shared__ float s_m[4][64], s_s[4][64], s_a[4][64];
     __shared__ float s_pool[64], s_big[256], s_head[8];
     __shared__ bool s_last;
@@ -209,6 +218,7 @@ __global__ void __launch_bounds__(POSE_THREADS) pose_head_kernel(const PoseParam
             whead[j] = hw_ < 4 ? __ldg(p.w_q + (ln + 32 * j) * 4 + hw_) : (hw_ < 7 ? __ldg(p.w_t + (ln + 32 * j) * 3 + (hw_ - 4)) : 0.f);
         bhead = hw_ < 4 ? __ldg(p.b_q + hw_) : (hw_ < 7 ? __ldg(p.b_t + (hw_ - 4)) : 0.f);
     }
+    pdl_wait();          // features / logits / coarse pose come from the kernels before
 
     // online masked softmax over this CTA's slice of the points, per channel; the slice is short
     // (<= 4 * POSE_PT points) and all of a thread's loads are issued before any of them is used
@@ -362,6 +372,8 @@ struct PyramidParams {
 
 __global__ void pyramid_xyz_kernel(const PyramidParams p)
 {
+    pdl_trigger();
+    pdl_wait();
     const long long per = p.start[4];
     const long long total = per * p.S;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
@@ -428,9 +440,7 @@ extern "C" int elo_pyramid_xyz(int samples, int H, int W, const int* out_h, cons
     long long blocks = (total + 255) / 256;
     const long long cap = (long long)device_info().sm_count * 8;
     if (blocks > cap) blocks = cap;
-    pyramid_xyz_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(p);
-    count_launches(1);
-    cudaError_t err = cudaGetLastError();
+    cudaError_t err = launch(pyramid_xyz_kernel, dim3((unsigned)blocks), dim3(256), 0, (cudaStream_t)stream, p);
     return err == cudaSuccess ? ELO_OK : set_cuda_error(err, "pyramid_xyz launch");
 }
 
@@ -472,12 +482,11 @@ extern "C" int elo_project(const elo_project_desc* d, void* stream)
         return (unsigned)(b < 1 ? 1 : (b > cap ? cap : b));
     };
     const long long cells = (long long)p.B * p.H * p.W;
-    project_init_kernel<<<blocks(cells * (p.C > 3 ? p.C : 3)), 256, 0, st>>>(p);
-    project_bin_kernel<<<blocks((long long)p.B * p.N), 256, 0, st>>>(p);
+    cudaError_t err = launch(project_init_kernel, dim3(blocks(cells * (p.C > 3 ? p.C : 3))), dim3(256), 0, st, p);
+    if (err == cudaSuccess) err = launch(project_bin_kernel, dim3(blocks((long long)p.B * p.N)), dim3(256), 0, st, p);
     const int slabs = 1 + (p.out_feat ? (p.C + 3) / 4 : 0);
-    project_scatter_kernel<<<blocks((long long)p.B * p.N * slabs), 256, 0, st>>>(p);
-    count_launches(3);
-    cudaError_t err = cudaGetLastError();
+    if (err == cudaSuccess)
+        err = launch(project_scatter_kernel, dim3(blocks((long long)p.B * p.N * slabs)), dim3(256), 0, st, p);
     return err == cudaSuccess ? ELO_OK : set_cuda_error(err, "project launch");
 }
 
@@ -500,8 +509,6 @@ extern "C" int elo_pose_head(const elo_pose_head_desc* d, void* stream)
     p.q_coarse = d->q_coarse; p.t_coarse = d->t_coarse; p.partial = d->partial; p.counter = d->counter;
     p.q_out = d->q_out; p.t_out = d->t_out; p.q_norm_out = d->q_norm_out; p.pooled_out = d->pooled_out;
     dim3 grid(p.G, p.B);
-    pose_head_kernel<<<grid, POSE_THREADS, 0, (cudaStream_t)stream>>>(p);
-    count_launches(1);
-    cudaError_t err = cudaGetLastError();
+    cudaError_t err = launch(pose_head_kernel, grid, dim3(POSE_THREADS), 0, (cudaStream_t)stream, p);
     return err == cudaSuccess ? ELO_OK : set_cuda_error(err, "pose_head launch");
 }

@@ -69,7 +69,9 @@ __global__ void __launch_bounds__(256) set_conv_small_kernel(const SmallParams p
     int* nbr_all = sc.take<int>(256);
 
     const Window g = p.g;
-    for (int i = threadIdx.x; i < NW; i += blockDim.x) wts[i] = __ldg(p.weights + i);
+    pdl_trigger();
+    for (int i = threadIdx.x; i < NW; i += blockDim.x) wts[i] = __ldg(p.weights + i);     // constants: before the wait
+    pdl_wait();
     build_offsets(off, p.random_hw[blockIdx.y], g.kt, g.kH, g.kW, blockDim.x);
     __syncthreads();
     const float* W1 = wts;
@@ -195,9 +197,7 @@ static int launch_small(const SmallParams& p, int nsets, cudaStream_t st)
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return set_cuda_error(e, "set_conv_small smem");
     }
-    kern<<<dim3((unsigned)ctas, nsets), (unsigned)wpc * 32, smem, st>>>(p);
-    count_launches(1);
-    cudaError_t err = cudaGetLastError();
+    cudaError_t err = launch(kern, dim3((unsigned)ctas, nsets), dim3((unsigned)wpc * 32), smem, st, p);
     return err == cudaSuccess ? ELO_OK : set_cuda_error(err, "set_conv_small launch");
 }
 

@@ -87,7 +87,10 @@ def get_model(point_cloud, H_input, W_input, T_gt, T_trans, T_trans_inv, is_trai
         T_gt = T_gt.to(dev) if T_gt is not None else eye
         q_gt, t_gt = mu.gt_pose(T_gt, eye if T_trans is None else T_trans.to(dev),
                                 eye if T_trans_inv is None else T_trans_inv.to(dev), aug_frame)
-        T_aug, T_apply = mu.aug_setup(eye if T_trans is None else T_trans, aug_frame, B, dev)
+        if T_trans is None and aug_frame is None:
+            T_aug, T_apply = store.default_aug(B)               # constants: no per-forward tensor ops
+        else:
+            T_aug, T_apply = mu.aug_setup(eye if T_trans is None else T_trans, aug_frame, B, dev)
         stride_pt = point_cloud.stride(1)
         xyz_in, _, _ = mu.project_points(point_cloud[:, :N, 0:3], None, H_input, W_input, mode=1, T=T_aug,
                                          T_apply=T_apply, inner_batch=B, outer_stride=N * stride_pt, batch_size=2 * B)

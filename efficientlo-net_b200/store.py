@@ -67,6 +67,15 @@ class ParamStore:
             self._cache[key] = torch.eye(4, device=self.device).expand(batch, 4, 4).contiguous()
         return self._cache[key]
 
+    def default_aug(self, batch):
+        """Constant (T (2B,4,4) identity, apply (2B,) = [0]*B + [1]*B): no augmentation matrix given, frame 2 is
+        the 'augmented' one (the reference's inference setting, main.py:311-312)."""
+        key = ("default_aug", batch)
+        if key not in self._cache:
+            apply = torch.cat([torch.zeros(batch, dtype=torch.int32), torch.ones(batch, dtype=torch.int32)])
+            self._cache[key] = (self.eye(2 * batch), apply.to(self.device))
+        return self._cache[key]
+
     def invalidate(self):
         self._cache.clear()
 

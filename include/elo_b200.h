@@ -76,6 +76,11 @@ int elo_fused_conv_random_k(int batch_size, int H, int W, int npoints, int kerne
  * The packed `weights` a descriptor carries must match the engine (packing.pack_stream_tc / pack_stream). */
 int elo_set_mlp_engine(int engine);
 int elo_get_mlp_engine(void);
+/* Programmatic dependent launch between the kernels of this library (default on; environment ELO_PDL=0
+ * turns it off): a kernel's prologue -- barrier / tensor-memory set-up, weight prefetch -- overlaps the
+ * tail of the kernel before it.  Results are identical either way. */
+int elo_set_pdl(int on);
+int elo_get_pdl(void);
 /* Debug: device buffer of 64 int64; CTA (0,0) of every tensor-core kernel launched afterwards writes phase
  * timestamps (ns, %globaltimer) into it: compute thread 0 -> [0,32), MMA thread -> [32,64).  NULL = off. */
 int elo_set_time_log(long long *device_buf);
