@@ -116,6 +116,10 @@ def lib():
         handle.elo_set_mlp_engine.restype = _c_int
         handle.elo_get_mlp_engine.argtypes = []
         handle.elo_get_mlp_engine.restype = _c_int
+        handle.elo_set_index_kernel.argtypes = [_c_int]
+        handle.elo_set_index_kernel.restype = _c_int
+        handle.elo_get_index_kernel.argtypes = []
+        handle.elo_get_index_kernel.restype = _c_int
         handle.elo_set_pdl.argtypes = [_c_int]
         handle.elo_set_pdl.restype = _c_int
         handle.elo_get_pdl.argtypes = []
@@ -160,6 +164,11 @@ def mlp_engine():
 
 def set_mlp_engine(engine):
     check(lib().elo_set_mlp_engine(int(engine)), "elo_set_mlp_engine")
+
+
+def set_index_kernel(which):
+    """0: choose by query count, 1: tile-staged thread-per-query kernel, 2: one warp per query."""
+    check(lib().elo_set_index_kernel(int(which)), "elo_set_index_kernel")
 
 
 def set_pdl(on):

@@ -182,6 +182,11 @@ __global__ void __launch_bounds__(256) multi_search_kernel(const __grid_constant
     }
 }
 
+// fused_conv_tiled.cu: thread-per-query kernel over a staged tile, for calls with many queries
+int launch_index_tiled(bool select, int B, int H, int W, int N, const Window& g, const float* xyz1, const float* xyz2,
+                       const int* idx_n2, const int* random_hw, int* out_idx, float* out_valid, float* out_vdis,
+                       float* out_mask, cudaStream_t stream, int* rc);
+
 static int launch_index(bool select, int B, int H, int W, int N, int kH, int kW, int K, int flag_copy,
                         float distance, int stride_h, int stride_w, const float* xyz1,
                         const float* xyz2, const int* idx_n2, const int* random_hw, int* out_idx,
@@ -217,6 +222,13 @@ static int launch_index(bool select, int B, int H, int W, int N, int kH, int kW,
     p.out_idx = out_idx; p.out_valid = out_valid; p.out_vdis = out_vdis; p.out_mask = out_mask;
     p.total = (long long)B * N;
     p.fast_ok = K <= 32 && p.g.d2max < 1e10f;
+
+    {
+        int rc = ELO_OK;
+        if (launch_index_tiled(select, B, H, W, N, p.g, xyz1, xyz2, idx_n2, random_hw, out_idx, out_valid, out_vdis,
+                               out_mask, stream, &rc))
+            return rc;
+    }
 
     int warps = 8;
     size_t smem = (size_t)kt * sizeof(int2);

@@ -76,6 +76,12 @@ int elo_fused_conv_random_k(int batch_size, int H, int W, int npoints, int kerne
  * The packed `weights` a descriptor carries must match the engine (packing.pack_stream_tc / pack_stream). */
 int elo_set_mlp_engine(int engine);
 int elo_get_mlp_engine(void);
+/* Work decomposition of the two stand-alone index ops (results are identical, bit for bit):
+ *   0 (default)  by size: calls with at least 2 x 64 queries per SM, K <= 32 and distance^2 < 1e10 take the
+ *                tile-staged thread-per-query kernel (fused_conv_tiled.cu), everything else one warp per query;
+ *   1            tiled whenever K <= 32 and distance^2 < 1e10;   2   always one warp per query. */
+int elo_set_index_kernel(int which);
+int elo_get_index_kernel(void);
 /* Programmatic dependent launch between the kernels of this library (default on; environment ELO_PDL=0
  * turns it off): a kernel's prologue -- barrier / tensor-memory set-up, weight prefetch -- overlaps the
  * tail of the kernel before it.  Results are identical either way. */

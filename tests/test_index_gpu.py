@@ -13,6 +13,15 @@ pytestmark = pytest.mark.gpu
 GOLDEN = os.path.join(os.path.dirname(__file__), "golden", "index_golden.npz")
 
 
+@pytest.fixture(autouse=True, params=["tiled", "warp"])
+def index_kernel(request, elo):
+    """Every test of this module runs on both work decompositions of the index ops: the tile-staged
+    thread-per-query kernel (fused_conv_tiled.cu) and one warp per query (fused_conv_index.cu)."""
+    elo._lib.set_index_kernel(1 if request.param == "tiled" else 2)
+    yield request.param
+    elo._lib.set_index_kernel(0)
+
+
 def run_cuda(elo, cuda, mode, xyz1, xyz2, idx_n2, random_hw, H, W, npoints, kH, kW, K, flag_copy,
              distance, sh, sw):
     fn = elo.fused_conv_select_k if mode == "select" else elo.fused_conv_random_k
@@ -75,6 +84,59 @@ def test_model_sites_vs_oracle_and_reference_kernel(elo, cuda, site):
             c[k] = torch.as_tensor(c[k]).to(cuda)
         ref = tuple(o.cpu().numpy() for o in cases.call(io.ref_gpu, c))
         cases.assert_same(got, ref, site[0] + " vs reference .cu")
+
+
+def raster_case(rng, mode, B, H, W, kH, kW, K, sh, sw, distance, flag_copy=0, holes=0.2, integer=False, n=None):
+    """Queries in raster order (how the model and BASELINE.json configs[0] call the ops): the staged-tile path."""
+    h2, w2 = -(-H // sh), -(-W // sw)
+    xyz1 = cases.range_image(rng, B, H, W, holes=holes, integer=integer)
+    xyz2 = xyz1.copy() if (sh == 1 and sw == 1 and rng.random() < 0.5) else cases.range_image(rng, B, h2, w2, holes=holes, integer=integer)
+    idx = cases.all_cells(B, H, W)
+    if n is not None:
+        idx = np.ascontiguousarray(idx[:, :n])
+    return dict(mode=mode, xyz1=xyz1, xyz2=xyz2, idx_n2=idx, random_hw=rng.permutation(kH * kW).astype(np.int32),
+                H=H, W=W, npoints=idx.shape[1], kernel_size_H=kH, kernel_size_W=kW, K=K, flag_copy=flag_copy,
+                distance=distance, stride_h=sh, stride_w=sw)
+
+
+RASTER = [
+    # B, H, W, kH, kW, K, sh, sw, distance, flag_copy, integer, n
+    (1, 16, 225, 11, 41, 6, 1, 1, 1000.0, 0, False, None),
+    (2, 8, 113, 7, 25, 6, 1, 1, 1000.0, 0, False, None),      # 904 queries: CTAs straddle the two samples
+    (2, 8, 113, 7, 15, 8, 2, 2, 6.0, 0, False, None),         # strided window centres
+    (1, 4, 57, 5, 35, 32, 1, 1, 1000.0, 1, False, None),
+    (3, 5, 21, 3, 9, 16, 1, 1, 3.0, 1, False, 77),            # window wider than half the cylinder, ragged N
+    (1, 9, 10, 5, 15, 4, 1, 1, 1000.0, 0, False, None),       # kW > W: every column seen more than once
+    (2, 12, 64, 7, 9, 16, 1, 3, 2.0, 1, True, None),          # integer grid: ties everywhere -> exact replay
+    (1, 32, 300, 9, 15, 32, 1, 1, 0.5, 0, False, None),
+    (1, 6, 40, 1, 1, 1, 1, 1, 1000.0, 0, False, None),
+    (1, 6, 40, 3, 3, 7, 1, 1, 1000.0, 1, True, 130),
+]
+
+
+@pytest.mark.parametrize("mode", ["select", "random"])
+@pytest.mark.parametrize("spec", RASTER, ids=lambda s: "B%d_%dx%d_k%dx%d_K%d_s%d%d" % s[:8])
+def test_raster_queries_vs_oracle(elo, cuda, mode, spec):
+    B, H, W, kH, kW, K, sh, sw, distance, flag_copy, integer, n = spec
+    rng = np.random.default_rng(abs(hash((mode,) + spec[:8])) % (2 ** 31))
+    case = raster_case(rng, mode, B, H, W, kH, kW, K, sh, sw, distance, flag_copy, integer=integer, n=n)
+    cases.assert_same(cases.call(cuda_impl(elo, cuda), case), cases.call(io.port, case, nthreads=8), "raster %s" % (spec,))
+
+
+def test_select_k_near_ties_take_the_exact_path(elo, cuda):
+    """Distances that differ only in the mantissa bits the packed keys give up for the walk position must
+    still come out in the reference's order (the tiled kernel replays such queries exactly)."""
+    H, W, kH, kW, K = 3, 96, 3, 31, 8
+    rng = np.random.default_rng(11)
+    xyz = np.zeros((1, H, W, 3), np.float32)
+    base = 1.0 + rng.integers(0, 6, size=(H, W)).astype(np.float32)          # few distinct ranges
+    xyz[0, :, :, 0] = base * (1.0 + rng.integers(0, 4, size=(H, W)).astype(np.float32) * 2.0 ** -21)
+    xyz[0, :, :, 1] = 0.25
+    idx = cases.all_cells(1, H, W)
+    case = dict(mode="select", xyz1=xyz, xyz2=xyz, idx_n2=idx, random_hw=rng.permutation(kH * kW).astype(np.int32),
+                H=H, W=W, npoints=H * W, kernel_size_H=kH, kernel_size_W=kW, K=K, flag_copy=0, distance=1000.0,
+                stride_h=1, stride_w=1)
+    cases.assert_same(cases.call(cuda_impl(elo, cuda), case), cases.call(io.port, case, nthreads=8), "near ties")
 
 
 def test_golden_vectors(elo, cuda):
