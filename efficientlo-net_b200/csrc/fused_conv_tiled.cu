@@ -5,22 +5,22 @@
 // tf_ops/2d_conv_select_k/fused_conv_g.cu:11-209, tf_ops/2d_conv_random_k/fused_conv_g.cu:13-156); the
 // difference is the work decomposition.  The warp-per-query kernel spends ~1600 warp instructions per
 // query (K rounds of a warp-wide arg-min) and is issue-bound at 0.10 of the HBM roofline.  Here:
-//   * a CTA owns TQ = 64 consecutive queries, one THREAD per query (like the reference) -- but
-//   * the searched grid's neighbourhood of the CTA (bounding box of the 64 window centres + the window
-//     halo, columns wrapped around the cylinder, rows outside the image as empty pixels) is staged ONCE in
-//     shared memory as three planes, so the inner loop is 3 conflict-free LDS + 9 FP32 ops per window cell
-//     with no wrap / bounds logic;
+//   * a CTA owns TQ = 128 / 160 / 192 consecutive queries, one THREAD per query (like the reference) -- but
+//   * the searched grid's neighbourhood of the CTA (bounding box of the window centres + the window halo,
+//     columns wrapped around the cylinder, rows outside the image as empty pixels) is staged ONCE in shared
+//     memory as one float4 per cell (x, y, z, empty?), so a window cell costs one conflict-free LDS.128 and
+//     ten FP32 operations, with no wrap / bounds / emptiness logic in the loop;
 //   * select-K keeps the K+1 smallest candidates as a sorted register array of PACKED keys (distance bits
 //     with the walk position in the low mantissa bits), maintained with a branch-free min/max chain.
 //     Candidates that beat the current (K+1)-th key are first pushed into a per-thread shared-memory
 //     queue; the chain runs once per queued item of the slowest lane, every 16 window cells, so a warp pays
 //     for max-over-lanes insertions instead of one insertion per window cell.  The window is walked
-//     centre-out (counting sort of dw^2 + 4 dh^2, per CTA) so the queue empties quickly: the result of a
-//     select-K does not depend on the walk order unless distances tie;
+//     centre-out (cells sorted by dw^2 + 4 dh^2 on the host, passed in the kernel parameters) so the queue
+//     empties quickly: the result of a select-K does not depend on the walk order unless distances tie;
 //   * two selected keys that agree in the bits left for the distance (a real tie or a near-tie) send that
 //     query to the exact swap-based replay of elo_search.cuh (warp-cooperative, inside the same CTA), which
 //     reproduces the reference's unstable tie order;
-//   * all four outputs of the CTA (contiguous in HBM: 64 rows of each tensor) are written with 16-byte
+//   * all four outputs of the CTA (contiguous in HBM: TQ rows of each tensor) are written with 16-byte
 //     stores whose values are decoded from per-query counts in shared memory -- the 2 x kt floats of
 //     valid_idx / valid_in_dis_idx per query are 83 % of the op's bytes.
 // A CTA whose queries are not spatially compact (arbitrary idx_n2), or that spans two samples, reads the
@@ -29,8 +29,10 @@
 #include <stdint.h>
 #include <stdlib.h>
 
+#include <algorithm>
 #include <atomic>
 #include <type_traits>
+#include <vector>
 
 #include "../../include/elo_b200.h"
 #include "elo_common.cuh"
@@ -38,8 +40,12 @@
 
 namespace elo {
 
-constexpr int TQ = 64;       // queries = threads per CTA
+// TQ queries = threads per CTA is a template parameter (128 / 160 / 192): the launcher picks the one that
+// spreads the call's CTAs most evenly over the SMs in a single wave (115 200 queries: 720 CTAs of 160,
+// five on 128 SMs and four on 20, instead of 900 CTAs of 128 with a seventh CTA on 12 SMs).
 constexpr int QG = 16;       // window cells between two drains of the candidate queue
+constexpr int LB = 8;        // staged cells loaded ahead of their use
+constexpr int MAX_WALK = 1024;               // window cells whose host-sorted walk fits the kernel parameters
 constexpr unsigned KEY_NONE = 0x7f000000u;   // larger than any accepted key (d <= distance^2 < 1e10)
 
 struct TiledParams {
@@ -55,15 +61,16 @@ struct TiledParams {
     float* out_mask;
     long long total;
     int tile_cap;        // cells the staged tile may hold
+    int tile_bytes;      // bytes of the tile region (also scratch of the exact replay)
     int jbits;           // low key bits that carry the walk position
-    int nbins;           // bins of the centre-out counting sort
     int vec_ok;          // every output pointer is 16-byte aligned
     unsigned magic_kt;   // ceil(2^32 / kt), ceil(2^32 / K): exact quotients for the writer's ranges
     unsigned magic_k;
+    int walk[MAX_WALK];  // select-K: window cells centre-out, (dh << 16) | (dw & 0xffff)
 };
 
 struct TileGeom {
-    int staged;          // 1: tile holds the neighbourhood; 0: read the grid directly
+    int staged;          // 1: tile holds the neighbourhood; 0: read the grid directly; -1: no valid centre
     int row0, col0;      // grid cell of tile cell (0, 0) (col0 may lie outside [0, w2): wrapped on load)
     int th, tw;
     int hmin, rmin;
@@ -99,45 +106,33 @@ __device__ __forceinline__ void chain_insert(unsigned (&a)[KR], unsigned x)
     }
 }
 
-template <bool SELECT, int KR>
-__global__ void __launch_bounds__(TQ) fused_conv_tiled_kernel(const TiledParams p)
+template <bool SELECT, int KR, int TQ>
+__global__ void __launch_bounds__(TQ, (KR <= 17 ? 896 / TQ : 512 / TQ)) fused_conv_tiled_kernel(const __grid_constant__ TiledParams p)
 {
+    constexpr int TW = TQ / 32;   // warps per CTA
     extern __shared__ __align__(16) unsigned char smem_raw[];
     pdl_trigger();
     pdl_wait();
-    const Window g = p.g;
+    const Window& g = p.g;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int kt = g.kt, K = g.K;
 
     // ---- shared-memory carve-up ------------------------------------------------------------------
     unsigned char* sp = smem_raw;
     auto take = [&](size_t bytes) { unsigned char* r = sp; sp += (bytes + 15) & ~size_t(15); return r; };
-    int2* off_scan = reinterpret_cast<int2*>(take((size_t)kt * 8));          // (dh, dw) in reference scan order
     int* walk_pk = reinterpret_cast<int*>(take((size_t)kt * 4));             // (dh << 16 | dw & 0xffff) in walk order
-    int* walk_to = reinterpret_cast<int*>(take((size_t)kt * 4));             // tile offset of the walk's j-th cell
-    int* sel = reinterpret_cast<int*>(take((size_t)K * TQ * 4));             // sel[s][tid]: packed (hh, ww) of slot s
-    unsigned* queue = reinterpret_cast<unsigned*>(take((size_t)QG * TQ * 4));
-    int* s_nvalid = reinterpret_cast<int*>(take(TQ * 4));
-    int* s_nsel = reinterpret_cast<int*>(take(TQ * 4));
+    int* walk_to = reinterpret_cast<int*>(take((size_t)kt * 4));             // byte offset of the walk's j-th cell in the tile
+    // candidate queue during a select-K walk; afterwards sel[s][tid] = packed (hh, ww) of output slot s
+    int* sel = reinterpret_cast<int*>(take((size_t)(K > QG ? K : QG) * TQ * 4));
+    unsigned* queue = reinterpret_cast<unsigned*>(sel);
+    float* s_nv = reinterpret_cast<float*>(take(TQ * 4));                    // leading ones of valid_idx
+    float* s_ns = reinterpret_cast<float*>(take(TQ * 4));                    // ... of valid_in_dis_idx
     int* s_nwr = reinterpret_cast<int*>(take(TQ * 4));
     int* s_first = reinterpret_cast<int*>(take(TQ * 4));
     int* s_bcopy = reinterpret_cast<int*>(take(TQ * 4));                     // b << 1 | copy
-    float4* s_ctr = reinterpret_cast<float4*>(take(TQ * 16));                // centre xyz (+ ch / cw as int bits)
-    int* s_chw = reinterpret_cast<int*>(take(TQ * 4));
     int* s_ties = reinterpret_cast<int*>(take(TQ * 4));
-    int* s_misc = reinterpret_cast<int*>(take(64));                          // reductions, tie count, geometry
-    float* fb_dist = nullptr;
-    int* fb_hw = nullptr;
-    int* bins = nullptr;
-    if (SELECT) {
-        fb_dist = reinterpret_cast<float*>(take((size_t)(TQ / 32) * kt * 4));
-        fb_hw = reinterpret_cast<int*>(take((size_t)(TQ / 32) * kt * 4));
-        bins = reinterpret_cast<int*>(take((size_t)(p.nbins + 1) * 4));
-    }
-    float* tile = reinterpret_cast<float*>(take((size_t)p.tile_cap * 12));
-    float* tx = tile;
-    float* ty = tile + p.tile_cap;
-    float* tz = tile + 2 * p.tile_cap;
+    int* s_misc = reinterpret_cast<int*>(take(64));                          // tie count, reference column, geometry
+    unsigned char* tile = take((size_t)p.tile_bytes);                        // float4 per cell; replay scratch later
 
     // ---- this thread's query -----------------------------------------------------------------------
     const long long q0 = (long long)blockIdx.x * TQ;
@@ -148,8 +143,8 @@ __global__ void __launch_bounds__(TQ) fused_conv_tiled_kernel(const TiledParams 
     bool cvalid = false;
     if (active) {
         b = (int)(q / p.N);
-        h = __ldg(p.idx_n2 + q * 2);
-        w = __ldg(p.idx_n2 + q * 2 + 1);
+        const int2 hw = __ldg(reinterpret_cast<const int2*>(p.idx_n2) + q);
+        h = hw.x; w = hw.y;
         if (h >= 0 && h < p.H && w >= 0 && w < p.W) {       // reference: out-of-range = UB; here: empty row
             const float* c = p.xyz1 + ((size_t)b * p.H * p.W + (size_t)h * p.W + w) * 3;
             xc = __ldg(c); yc = __ldg(c + 1); zc = __ldg(c + 2);
@@ -157,20 +152,12 @@ __global__ void __launch_bounds__(TQ) fused_conv_tiled_kernel(const TiledParams 
         }
     }
     const int ch = h / g.stride_h, cw = w / g.stride_w;
-
-    // ---- tables: scan order, and (select-K) the centre-out walk -----------------------------------------
     const int hh2 = g.kH / 2, hw2 = g.kW / 2;
-    if (tid < 16) s_misc[tid] = tid == 1 ? min(max(cw, 0), g.w2 - 1) : 0;   // [0] tie count, [1] reference column (query 0)
-    if (SELECT)
-        for (int i = tid; i <= p.nbins; i += TQ) bins[i] = 0;
-    for (int j = tid; j < kt; j += TQ) {
-        const int pp = __ldg(p.random_hw + j);
-        off_scan[j] = make_int2(pp / g.kW - hh2, pp % g.kW - hw2);
-    }
+    if (tid < 16) s_misc[tid] = tid == 1 ? min(max(cw, 0), g.w2 - 1) : 0;   // [0] tie count, [1] reference column
     __syncthreads();
 
     // ---- geometry of the CTA's neighbourhood --------------------------------------------------------------
-    // columns are measured relative to the first query's centre and folded onto (-w2/2, w2/2], so a run of
+    // columns are measured relative to one query's centre and folded onto [-w2/2, w2/2], so a run of
     // queries that crosses the end of an image row is still one compact box on the cylinder
     const int cwref = s_misc[1];
     int rel = cw - cwref;
@@ -196,7 +183,7 @@ __global__ void __launch_bounds__(TQ) fused_conv_tiled_kernel(const TiledParams 
             TileGeom tg;
             int ok = 1;
             hmin = big; hmax = -big; rmin = big; rmax = -big; bmin = big; bmax = -big;
-            for (int wv = 0; wv < TQ / 32; ++wv) {
+            for (int wv = 0; wv < TW; ++wv) {
                 const int* r = red + wv * 8;
                 hmin = min(hmin, r[0]); hmax = max(hmax, r[1]);
                 rmin = min(rmin, r[2]); rmax = max(rmax, r[3]);
@@ -214,7 +201,7 @@ __global__ void __launch_bounds__(TQ) fused_conv_tiled_kernel(const TiledParams 
                     tg.row0 = hmin - hh2; tg.col0 = cwref + rmin - hw2;
                 }
             } else {
-                tg.staged = -1;                       // no valid centre in this CTA: nothing to search
+                tg.staged = -1;
             }
             *reinterpret_cast<TileGeom*>(s_misc + 4) = tg;
         }
@@ -225,71 +212,48 @@ __global__ void __launch_bounds__(TQ) fused_conv_tiled_kernel(const TiledParams 
     const int tw = tg.tw;
 
     if (tg.staged >= 0) {
-        // ---- stage the tile -------------------------------------------------------------------------
+        // ---- stage the tile: (x, y, z, 1 if the pixel is empty) ---------------------------------------------
         if (staged) {
             const float* g2 = p.xyz2 + (size_t)tg.b * g.h2 * g.w2 * 3;
-            const int cells = tg.th * tw;
+            float4* t4 = reinterpret_cast<float4*>(tile);
             int c0 = tg.col0 % g.w2;
             if (c0 < 0) c0 += g.w2;
-            for (int i = tid; i < cells; i += TQ) {
-                const int r = i / tw, c = i - r * tw;
-                const int gr = tg.row0 + r;
+            for (int c = tid; c < tw; c += TQ) {
                 const int gc = (c0 + c) % g.w2;
-                float x = 0.f, y = 0.f, z = 0.f;
-                if (gr >= 0 && gr < g.h2) {
-                    const float* s = g2 + ((size_t)gr * g.w2 + gc) * 3;
-                    x = __ldg(s); y = __ldg(s + 1); z = __ldg(s + 2);
+                for (int r = 0; r < tg.th; ++r) {
+                    const int gr = tg.row0 + r;
+                    float x = 0.f, y = 0.f, z = 0.f;
+                    if (gr >= 0 && gr < g.h2) {
+                        const float* s = g2 + ((size_t)gr * g.w2 + gc) * 3;
+                        x = __ldg(s); y = __ldg(s + 1); z = __ldg(s + 2);
+                    }
+                    // empty pixel (reference :98-104); FSETP.GTU there: a NaN pixel counts as a point
+                    t4[r * tw + c] = make_float4(x, y, z, sq3(x, y, z) <= 1e-10f ? 1.0f : 0.0f);
                 }
-                tx[i] = x; ty[i] = y; tz[i] = z;
             }
         }
         // ---- walk tables ----------------------------------------------------------------------------------
-        if (SELECT) {
-            // centre-out: counting sort of the window cells by dw^2 + 4 dh^2 (scaled into nbins bins)
-            const int kmax = hw2 * hw2 + 4 * hh2 * hh2;
-            int shift = 0;
-            while ((kmax >> shift) >= p.nbins) ++shift;
-            for (int c = tid; c < kt; c += TQ) {
-                const int dh = c / g.kW - hh2, dw = c % g.kW - hw2;
-                atomicAdd(&bins[((dw * dw + 4 * dh * dh) >> shift) + 1], 1);
+        for (int j = tid; j < kt; j += TQ) {
+            int r, cc;
+            if (SELECT) {
+                const int pk = p.walk[j];
+                r = (pk >> 16) + hh2; cc = (int)(short)(pk & 0xffff) + hw2;
+            } else {
+                const int pp = __ldg(p.random_hw + j);
+                r = pp / g.kW; cc = pp - r * g.kW;
             }
-            __syncthreads();
-            if (warp == 0) {       // inclusive scan of bins[1..nbins] -> bins[i] = first position of bin i
-                int run = 0;
-                for (int base = 1; base <= p.nbins; base += 32) {
-                    const int i = base + lane;
-                    int v = i <= p.nbins ? bins[i] : 0;
-#pragma unroll
-                    for (int d = 1; d < 32; d <<= 1) {
-                        const int t = __shfl_up_sync(FULL_MASK, v, d);
-                        if (lane >= d) v += t;
-                    }
-                    if (i <= p.nbins) bins[i] = run + v;
-                    run += __shfl_sync(FULL_MASK, v, 31);
-                }
-            }
-            __syncthreads();
-            for (int c = tid; c < kt; c += TQ) {
-                const int r = c / g.kW, cc = c % g.kW;
-                const int dh = r - hh2, dw = cc - hw2;
-                const int pos = atomicAdd(&bins[(dw * dw + 4 * dh * dh) >> shift], 1);
-                walk_pk[pos] = (dh << 16) | (dw & 0xffff);
-                walk_to[pos] = r * tw + cc;
-            }
-        } else {
-            for (int j = tid; j < kt; j += TQ) {
-                const int2 o = off_scan[j];
-                walk_pk[j] = (o.x << 16) | (o.y & 0xffff);
-                walk_to[j] = (o.x + hh2) * tw + (o.y + hw2);
-            }
+            walk_pk[j] = ((r - hh2) << 16) | ((cc - hw2) & 0xffff);
+            walk_to[j] = (r * tw + cc) * 16;
         }
         __syncthreads();
 
         // ---- the walk -----------------------------------------------------------------------------------
         const float* g2 = p.xyz2 + (size_t)b * g.h2 * g.w2 * 3;
-        int base = 0;
-        if (staged && cvalid) base = (ch - tg.hmin) * tw + (rel - tg.rmin);
+        const unsigned char* tb = tile;
+        if (staged && cvalid) tb += ((ch - tg.hmin) * tw + (rel - tg.rmin)) * 16;
+        const float d2l = cvalid ? g.d2max : -1.0f;       // an invalid centre accepts nothing
         int nvalid = 0, nsel = 0;
+        float ninv = 0.f, nrej = 0.f;     // staged walk: empty / rejected cells, counted on the FP32 pipe
         auto cell_of = [&](int j) {
             const int pk = walk_pk[j];
             return pack_hw(ch + (pk >> 16), wrap_once(cw + (int)(short)(pk & 0xffff), g.w2));
@@ -298,62 +262,99 @@ __global__ void __launch_bounds__(TQ) fused_conv_tiled_kernel(const TiledParams 
         // ST = std::true_type: the window cells come from the staged tile; false_type: straight from the grid
         auto walk = [&](auto ST) {
             constexpr bool STG = decltype(ST)::value;
-            // cell j of the walk (tile offset `to` when staged) -> (valid, accepted, distance)
-            auto eval = [&](int j, int to, bool& valid, bool& acc, float& d) {
-                float xq, yq, zq;
-                bool inb = true;
+            // cell j of the walk (tile offset `to` when staged) -> accepted?, distance; counts the valid cells
+            auto eval = [&](int j, int to, bool& acc, float& d) {
                 if constexpr (STG) {
-                    const int t = base + to;
-                    xq = tx[t]; yq = ty[t]; zq = tz[t];
+                    const float4 c = *reinterpret_cast<const float4*>(tb + to);
+                    ninv += c.w;
+                    d = fmaxf(sq3(__fsub_rn(xc, c.x), __fsub_rn(yc, c.y), __fsub_rn(zc, c.z)), 1e-10f);
+                    const float de = __fmaf_rn(c.w, 1e30f, d);    // + 0 for a point, + 1e30 for an empty pixel
+                    acc = !(de > d2l);
+                    if constexpr (SELECT) nrej += de > d2l ? 1.0f : 0.0f;
                 } else {
                     const int pk = walk_pk[j];
                     const int hh = ch + (pk >> 16);
                     const int ww = wrap_once(cw + (int)(short)(pk & 0xffff), g.w2);
-                    inb = hh >= 0 && hh < g.h2 && ww >= 0 && ww < g.w2;
-                    xq = yq = zq = 0.f;
+                    const bool inb = hh >= 0 && hh < g.h2 && ww >= 0 && ww < g.w2;
+                    float xq = 0.f, yq = 0.f, zq = 0.f;
                     if (inb && cvalid) {
                         const float* s = g2 + ((size_t)hh * g.w2 + ww) * 3;
                         xq = __ldg(s); yq = __ldg(s + 1); zq = __ldg(s + 2);
                     }
+                    const bool valid = cvalid && inb && !(sq3(xq, yq, zq) <= 1e-10f);
+                    nvalid += valid;
+                    d = fmaxf(sq3(__fsub_rn(xc, xq), __fsub_rn(yc, yq), __fsub_rn(zc, zq)), 1e-10f);
+                    acc = valid && !(d > g.d2max);
                 }
-                valid = cvalid && inb && !(sq3(xq, yq, zq) <= 1e-10f);   // FSETP.GTU in the reference: NaN is valid
-                d = fmaxf(sq3(__fsub_rn(xc, xq), __fsub_rn(yc, yq), __fsub_rn(zc, zq)), 1e-10f);
-                acc = valid && !(d > g.d2max);
             };
 
             if constexpr (SELECT) {
                 unsigned a[KR];
 #pragma unroll
                 for (int i = 0; i < KR; ++i) a[i] = KEY_NONE;
-                const unsigned jmask = (1u << p.jbits) - 1u;
+                const unsigned jmask = (1u << p.jbits) - 1u, nmask = ~jmask;     // jbits >= 4: QG positions fit
                 unsigned thr = KEY_NONE;
-                int cnt = 0;
-                auto visit = [&](int j, int to) {
-                    bool valid, acc; float d;
-                    eval(j, to, valid, acc, d);
-                    nvalid += valid; nsel += acc;
-                    const unsigned key = (__float_as_uint(d) & ~jmask) | (unsigned)j;
-                    if (acc && key < thr) { queue[cnt * TQ + tid] = key; ++cnt; }
+                unsigned* const qbase = queue + tid;
+                unsigned* qp = qbase;
+                // The key pushed by the filter carries only the position inside the group (a compile-time
+                // constant in the unrolled loop); the group base is OR-ed in when the queue is drained.  The
+                // filter may therefore mis-order a candidate against the current last key only when their
+                // distance bits are equal, which can change nothing but WHICH of two equal-distance keys sits
+                // in the last place -- and that is never output nor does it alter the near-tie test.
+                // `c` = the staged cell (ignored on the direct path, which loads inside eval_direct)
+                auto visit = [&](int jj, int j, const float4& c) {
+                    bool acc; float d;
+                    if constexpr (STG) {
+                        ninv += c.w;
+                        d = fmaxf(sq3(__fsub_rn(xc, c.x), __fsub_rn(yc, c.y), __fsub_rn(zc, c.z)), 1e-10f);
+                        const float de = __fmaf_rn(c.w, 1e30f, d);    // + 0 for a point, + 1e30 for an empty pixel
+                        acc = !(de > d2l);
+                        nrej += de > d2l ? 1.0f : 0.0f;
+                    } else {
+                        eval(j, 0, acc, d);
+                        nsel += acc;
+                    }
+                    const unsigned key = (__float_as_uint(d) & nmask) | (unsigned)jj;
+                    if (acc && key < thr) { *qp = key; qp += TQ; }
                 };
                 for (int jb = 0; jb < kt; jb += QG) {
                     if (jb + QG <= kt) {
+                        // the loads of LB cells are issued together, ahead of the queue stores the compiler
+                        // would otherwise have to keep them behind (shared memory may alias)
 #pragma unroll
-                        for (int j4 = 0; j4 < QG; j4 += 4) {
-                            const int4 to = *reinterpret_cast<const int4*>(walk_to + jb + j4);
-                            visit(jb + j4, to.x); visit(jb + j4 + 1, to.y); visit(jb + j4 + 2, to.z); visit(jb + j4 + 3, to.w);
+                        for (int j8 = 0; j8 < QG; j8 += LB) {
+                            float4 c[LB];
+                            if constexpr (STG) {
+#pragma unroll
+                                for (int i = 0; i < LB; i += 4) {
+                                    const int4 to = *reinterpret_cast<const int4*>(walk_to + jb + j8 + i);
+                                    c[i] = *reinterpret_cast<const float4*>(tb + to.x);
+                                    c[i + 1] = *reinterpret_cast<const float4*>(tb + to.y);
+                                    c[i + 2] = *reinterpret_cast<const float4*>(tb + to.z);
+                                    c[i + 3] = *reinterpret_cast<const float4*>(tb + to.w);
+                                }
+                            }
+#pragma unroll
+                            for (int i = 0; i < LB; ++i) visit(j8 + i, jb + j8 + i, c[i]);
                         }
                     } else {
-                        for (int j = jb; j < kt; ++j) visit(j, walk_to[j]);
+                        for (int j = jb; j < kt; ++j) {
+                            float4 c = make_float4(0.f, 0.f, 0.f, 0.f);
+                            if constexpr (STG) c = *reinterpret_cast<const float4*>(tb + walk_to[j]);
+                            visit(j - jb, j, c);
+                        }
                     }
                     // drain: one insertion per queued key of the slowest lane
+                    const int cnt = (int)(qp - qbase) / TQ;
                     const int n = __reduce_max_sync(FULL_MASK, cnt);
                     for (int t = 0; t < n; ++t) {
-                        const unsigned x = t < cnt ? queue[t * TQ + tid] : 0xffffffffu;
+                        const unsigned x = t < cnt ? (qbase[t * TQ] | (unsigned)jb) : 0xffffffffu;
                         chain_insert<KR>(a, x);
                     }
-                    cnt = 0;
+                    qp = qbase;
                     thr = a[KR - 1];
                 }
+                if constexpr (STG) nsel = kt - (int)nrej;
                 // near-ties among the K nearest (and against the first one left out) -> exact replay
                 const int nw = min(nsel, K);
                 bool tie = false;
@@ -379,63 +380,73 @@ __global__ void __launch_bounds__(TQ) fused_conv_tiled_kernel(const TiledParams 
                 int first = 0;
                 for (int j = 0; j < kt; ++j) {
                     if (!done) {
-                        bool valid, acc; float d;
-                        eval(j, walk_to[j], valid, acc, d);
-                        nvalid += valid;
+                        bool acc; float d;
+                        eval(j, walk_to[j], acc, d);
                         if (acc) {
                             const int c = cell_of(j);
                             if (nsel == 0) first = c;
                             sel[nsel * TQ + tid] = c;
                             ++nsel;
-                            done = nsel >= K;                 // the reference's break (:149-150)
+                            if (nsel >= K) {                  // the reference's break (:149-150): cells after
+                                done = true;                  // this one are not counted
+                                if constexpr (STG) nvalid = j + 1 - (int)ninv;
+                            }
                         }
                     }
                     if (__all_sync(FULL_MASK, done)) break;
                 }
+                if constexpr (STG) {
+                    if (!done) nvalid = kt - (int)ninv;
+                }
                 s_nwr[tid] = nsel;
                 s_first[tid] = first;
             }
+            if constexpr (STG && SELECT) nvalid = kt - (int)ninv;
         };
         if (staged) walk(std::true_type{});
         else walk(std::false_type{});
-        s_nvalid[tid] = nvalid;
-        s_nsel[tid] = nsel;
+        if (!cvalid) { nvalid = 0; nsel = 0; }
+        s_nv[tid] = (float)nvalid;
+        s_ns[tid] = (float)nsel;
         // select-K duplicates entry 0 even when nothing was in range (mask 1, index (b,0,0)); random-K only
         // once a first neighbour was accepted (reference select :180-192, random :126-138)
         s_bcopy[tid] = (b << 1) | ((cvalid && g.flag_copy == 1 && (SELECT || nsel > 0)) ? 1 : 0);
-        if (SELECT) {
-            s_ctr[tid] = make_float4(xc, yc, zc, 0.f);
-            s_chw[tid] = pack_hw(ch, cw);
-        }
         __syncthreads();
 
         // ---- exact replay of the tied queries (warp-cooperative, reference scan order) ---------------------
         if (SELECT) {
             const int nties = s_misc[0];
-            float* dist = fb_dist + (size_t)warp * kt;
-            int* hwv = fb_hw + (size_t)warp * kt;
-            for (int t = warp; t < nties; t += TQ / 32) {
-                const int qt = s_ties[t];
-                const float4 c = s_ctr[qt];
-                const int chw = s_chw[qt];
-                const int bq = s_bcopy[qt] >> 1;
-                const float* g2q = p.xyz2 + (size_t)bq * g.h2 * g.w2 * 3;
-                auto emit = [&](int slot, int hh, int ww) { sel[slot * TQ + qt] = pack_hw(hh, ww); };
-                int written = 0;
-                const SearchCounts sc = search_select_k(g2q, off_scan, g, chw >> 16, chw & 0xffff, c.x, c.y, c.z, dist,
-                                                        hwv, &written, emit);
-                __syncwarp();
-                if (lane == 0) { s_nwr[qt] = written; s_first[qt] = sc.first; }
-                __syncwarp();
+            if (nties > 0) {
+                // the tile is no longer needed: scan-order offsets + per-warp scratch live there now
+                int2* off_scan = reinterpret_cast<int2*>(tile);
+                float* dist = reinterpret_cast<float*>(tile + (size_t)kt * 8) + (size_t)warp * kt;
+                int* hwv = reinterpret_cast<int*>(tile + (size_t)kt * 8 + (size_t)TW * kt * 4) + (size_t)warp * kt;
+                build_offsets(off_scan, p.random_hw, kt, g.kH, g.kW, TQ);
+                __syncthreads();
+                for (int t = warp; t < nties; t += TW) {
+                    const int qt = s_ties[t];
+                    const long long gq = q0 + qt;
+                    const int bq = (int)(gq / p.N);
+                    const int2 hwq = __ldg(reinterpret_cast<const int2*>(p.idx_n2) + gq);
+                    const float* c = p.xyz1 + ((size_t)bq * p.H * p.W + (size_t)hwq.x * p.W + hwq.y) * 3;
+                    const float* g2q = p.xyz2 + (size_t)bq * g.h2 * g.w2 * 3;
+                    auto emit = [&](int slot, int hh, int ww) { sel[slot * TQ + qt] = pack_hw(hh, ww); };
+                    int written = 0;
+                    const SearchCounts sc = search_select_k(g2q, off_scan, g, hwq.x / g.stride_h, hwq.y / g.stride_w, __ldg(c),
+                                                            __ldg(c + 1), __ldg(c + 2), dist, hwv, &written, emit);
+                    __syncwarp();
+                    if (lane == 0) { s_nwr[qt] = written; s_first[qt] = sc.first; }
+                    __syncwarp();
+                }
+                __syncthreads();
             }
-            __syncthreads();
         }
     } else {
-        s_nvalid[tid] = 0; s_nsel[tid] = 0; s_nwr[tid] = 0; s_first[tid] = 0; s_bcopy[tid] = b << 1;
+        s_nv[tid] = 0.f; s_ns[tid] = 0.f; s_nwr[tid] = 0; s_first[tid] = 0; s_bcopy[tid] = b << 1;
         __syncthreads();
     }
 
-    // ---- write the CTA's 64 rows of every output ------------------------------------------------------------
+    // ---- write the CTA's TQ rows of every output ------------------------------------------------------------
     const int nq = (int)min((long long)TQ, p.total - q0);
     // slot `sl` of the CTA (query sl / K, slot sl % K) -> (b, hh, ww) and mask
     auto slot_value = [&](unsigned sl, int& vb, int& vh, int& vw, float& vm) {
@@ -472,32 +483,48 @@ __global__ void __launch_bounds__(TQ) fused_conv_tiled_kernel(const TiledParams 
         }
     }
     if (p.out_valid != nullptr || p.out_vdis != nullptr) {
+        // valid_idx / valid_in_dis_idx rows are a run of ones followed by zeros.  Four rows are kt float4s,
+        // 16-byte aligned; a thread keeps the same float4 column f for every block of four rows, so which
+        // rows its four elements belong to (at most two when kt >= 4) and their positions are loop-invariant,
+        // and an element is saturate(count - position): one FADD.SAT on the FP32 pipe per element and row.
         float* o_valid = p.out_valid ? p.out_valid + q0 * kt : nullptr;
         float* o_vdis = p.out_vdis ? p.out_vdis + q0 * kt : nullptr;
-        const unsigned nel = (unsigned)nq * kt;
-        const unsigned nvec = p.vec_ok ? nel / 4 : 0;
-        for (unsigned v = tid; v < nvec; v += TQ) {
-            unsigned pos;
-            unsigned r = udiv_magic(v * 4, p.magic_kt, (unsigned)kt, pos);
-            float a4[4], d4[4];
-            int nv = s_nvalid[r], ns = s_nsel[r];
+        const int nblk = (p.vec_ok && kt >= 4) ? nq / 4 : 0;
+        for (int f = tid; f < kt && nblk > 0; f += TQ) {
+            unsigned pos0, pos3;
+            const int r0 = (int)udiv_magic(4u * f, p.magic_kt, (unsigned)kt, pos0);
+            const int r3 = (int)udiv_magic(4u * f + 3u, p.magic_kt, (unsigned)kt, pos3);
+            // element i sits in row r0 at pos0 + i while that is < kt, else in row r3 at pos0 + i - kt
+            float pa[4], pb[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                a4[i] = (int)pos < nv ? 1.0f : 0.0f;
-                d4[i] = (int)pos < ns ? 1.0f : 0.0f;
-                if (++pos == (unsigned)kt) {
-                    pos = 0; ++r;
-                    if (i < 3) { nv = s_nvalid[r & (TQ - 1)]; ns = s_nsel[r & (TQ - 1)]; }
-                }
+                const bool lo = (int)pos0 + i < kt;
+                pa[i] = lo ? (float)((int)pos0 + i) : 1e9f;
+                pb[i] = lo ? 1e9f : (float)((int)pos0 + i - kt);
             }
-            if (o_valid) reinterpret_cast<float4*>(o_valid)[v] = make_float4(a4[0], a4[1], a4[2], a4[3]);
-            if (o_vdis) reinterpret_cast<float4*>(o_vdis)[v] = make_float4(d4[0], d4[1], d4[2], d4[3]);
+            float4* ov = o_valid ? reinterpret_cast<float4*>(o_valid) + f : nullptr;
+            float4* od = o_vdis ? reinterpret_cast<float4*>(o_vdis) + f : nullptr;
+            const float* nva = s_nv + r0; const float* nvb = s_nv + r3;
+            const float* nsa = s_ns + r0; const float* nsb = s_ns + r3;
+#pragma unroll 2
+            for (int blk = 0; blk < nblk; ++blk) {
+                const float va = nva[4 * blk], vb = nvb[4 * blk], da = nsa[4 * blk], db = nsb[4 * blk];
+                float a4[4], d4[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    a4[i] = __saturatef(va - pa[i]) + __saturatef(vb - pb[i]);
+                    d4[i] = __saturatef(da - pa[i]) + __saturatef(db - pb[i]);
+                }
+                if (ov) ov[(size_t)blk * kt] = make_float4(a4[0], a4[1], a4[2], a4[3]);
+                if (od) od[(size_t)blk * kt] = make_float4(d4[0], d4[1], d4[2], d4[3]);
+            }
         }
-        for (unsigned e = nvec * 4 + tid; e < nel; e += TQ) {
+        const unsigned nel = (unsigned)nq * kt;
+        for (unsigned e = (unsigned)nblk * 4u * kt + tid; e < nel; e += TQ) {
             unsigned pos;
             const unsigned r = udiv_magic(e, p.magic_kt, (unsigned)kt, pos);
-            if (o_valid) o_valid[e] = (int)pos < s_nvalid[r] ? 1.0f : 0.0f;
-            if (o_vdis) o_vdis[e] = (int)pos < s_nsel[r] ? 1.0f : 0.0f;
+            if (o_valid) o_valid[e] = (float)pos < s_nv[r] ? 1.0f : 0.0f;
+            if (o_vdis) o_vdis[e] = (float)pos < s_ns[r] ? 1.0f : 0.0f;
         }
     }
 }
@@ -510,16 +537,36 @@ static unsigned magic_of(unsigned d)
     return (unsigned)(((1ull << 32) + d - 1) / d);
 }
 
-template <bool SELECT, int KR>
+template <bool SELECT, int KR, int TQ>
 static cudaError_t launch_tiled_kr(const TiledParams& p, size_t smem, cudaStream_t stream)
 {
-    auto kern = fused_conv_tiled_kernel<SELECT, KR>;
+    auto kern = fused_conv_tiled_kernel<SELECT, KR, TQ>;
     if (smem > 48 * 1024) {
         cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (err != cudaSuccess) return err;
     }
     const long long ctas = (p.total + TQ - 1) / TQ;
     return launch(kern, dim3((unsigned)ctas), dim3(TQ), smem, stream, p);
+}
+
+template <int TQ>
+static cudaError_t launch_tiled_tq(bool select, const TiledParams& p, size_t smem, cudaStream_t stream)
+{
+    if (!select) return launch_tiled_kr<false, 1, TQ>(p, smem, stream);
+    if (p.g.K <= 6) return launch_tiled_kr<true, 7, TQ>(p, smem, stream);
+    if (p.g.K <= 16) return launch_tiled_kr<true, 17, TQ>(p, smem, stream);
+    return launch_tiled_kr<true, 33, TQ>(p, smem, stream);
+}
+
+static size_t tiled_smem(const Window& g, bool select, int tq, int* tile_cap, int* tile_bytes)
+{
+    auto up = [](size_t b) { return (b + 15) & ~size_t(15); };
+    // raster-order queries: tq centres on one or two rows (fewer columns when the window centre is strided)
+    *tile_cap = (g.kH + 1) * (tq + g.kW);
+    size_t tb = (size_t)*tile_cap * 16;
+    if (select) tb = std::max(tb, (size_t)g.kt * 8 + 2 * (size_t)(tq / 32) * g.kt * 4);   // replay scratch
+    *tile_bytes = (int)up(tb);
+    return 2 * up((size_t)g.kt * 4) + up((size_t)std::max(g.K, QG) * tq * 4) + 6 * up((size_t)tq * 4) + up(64) + (size_t)*tile_bytes;
 }
 
 // Returns 1 when the tiled kernel took the call (status in *rc), 0 when the caller should use the
@@ -533,39 +580,60 @@ int launch_index_tiled(bool select, int B, int H, int W, int N, const Window& g,
     const int force = g_index_kernel.load(std::memory_order_relaxed);
     if (force == 2) return 0;
     if (g.K > 32 || !(g.d2max < 1e10f)) return 0;
-    if (force != 1 && total < (long long)dev.sm_count * TQ * 2) return 0;   // too few threads to fill the chip
+    if (force != 1 && total < (long long)dev.sm_count * 128 * 2) return 0;   // too few threads to fill the chip
+    if (select && g.kt > MAX_WALK) return 0;
 
     TiledParams p;
     p.B = B; p.H = H; p.W = W; p.N = N; p.g = g;
     p.xyz1 = xyz1; p.xyz2 = xyz2; p.idx_n2 = idx_n2; p.random_hw = random_hw;
     p.out_idx = out_idx; p.out_valid = out_valid; p.out_vdis = out_vdis; p.out_mask = out_mask;
     p.total = total;
-    p.jbits = 1;
+    p.jbits = 4;
     while ((1 << p.jbits) < g.kt) ++p.jbits;
-    p.nbins = 512;
-    // raster-order queries: TQ centres on one or two rows (fewer columns when the window centre is strided)
-    const long long cap = (long long)(g.kH + 1) * (TQ + g.kW);
-    p.tile_cap = (int)cap;
     auto aligned = [](const void* q) { return q == nullptr || (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
     p.vec_ok = aligned(out_idx) && aligned(out_valid) && aligned(out_vdis) && aligned(out_mask) ? 1 : 0;
     p.magic_kt = magic_of((unsigned)g.kt);
     p.magic_k = magic_of((unsigned)g.K);
+    if (select) {
+        // centre-out walk: nearest pixels first, rows weighted 2x (a LiDAR's rows are ~2x further apart than
+        // its columns), so the K-th key tightens early and few later cells pass the filter
+        const int hh2 = g.kH / 2, hw2 = g.kW / 2;
+        std::vector<std::pair<int, int>> order((size_t)g.kt);
+        for (int c = 0; c < g.kt; ++c) {
+            const int dh = c / g.kW - hh2, dw = c % g.kW - hw2;
+            order[c] = std::make_pair(dw * dw + 4 * dh * dh, c);
+        }
+        std::sort(order.begin(), order.end());
+        for (int j = 0; j < g.kt; ++j) {
+            const int c = order[j].second;
+            p.walk[j] = ((c / g.kW - hh2) << 16) | ((c % g.kW - hw2) & 0xffff);
+        }
+    }
 
-    auto up = [](size_t b) { return (b + 15) & ~size_t(15); };
-    size_t smem = up((size_t)g.kt * 8) + 2 * up((size_t)g.kt * 4) + up((size_t)g.K * TQ * 4) + up((size_t)QG * TQ * 4) +
-                  5 * up(TQ * 4) + up(TQ * 16) + 2 * up(TQ * 4) + up(64);
-    if (select) smem += 2 * up((size_t)(TQ / 32) * g.kt * 4) + up((size_t)(p.nbins + 1) * 4);
-    smem += up((size_t)p.tile_cap * 12);
-    if (smem > 96 * 1024) return 0;
+    // CTA size: the candidate whose CTAs all fit on the chip at once and load the SMs most evenly
+    const int regs_cta_limit = (select && g.K > 16) ? 512 : 896;     // threads per SM the register budget allows
+    int best_tq = 0;
+    double best_cost = 0.0;
+    size_t best_smem = 0;
+    for (int tq : {128, 160, 192}) {
+        int cap, tb;
+        const size_t smem = tiled_smem(g, select, tq, &cap, &tb);
+        if (smem > 100 * 1024) continue;
+        const long long ctas = (total + tq - 1) / tq;
+        const long long per_sm = std::min<long long>((long long)((dev.max_smem_optin + 1024) / (smem + 1024)), regs_cta_limit / tq);
+        if (per_sm < 1) continue;
+        const long long rounds = (ctas + dev.sm_count - 1) / dev.sm_count;     // CTAs the busiest SM runs
+        double cost = (double)rounds * tq;                                      // queries on the busiest SM
+        if (ctas > per_sm * dev.sm_count) cost *= 1.25;                         // a second wave starts late
+        if (best_tq == 0 || cost < best_cost) { best_tq = tq; best_cost = cost; best_smem = smem; }
+    }
+    if (best_tq == 0) return 0;
+    tiled_smem(g, select, best_tq, &p.tile_cap, &p.tile_bytes);
 
     cudaError_t err;
-    if (select) {
-        if (g.K <= 6) err = launch_tiled_kr<true, 7>(p, smem, stream);
-        else if (g.K <= 16) err = launch_tiled_kr<true, 17>(p, smem, stream);
-        else err = launch_tiled_kr<true, 33>(p, smem, stream);
-    } else {
-        err = launch_tiled_kr<false, 1>(p, smem, stream);
-    }
+    if (best_tq == 128) err = launch_tiled_tq<128>(select, p, best_smem, stream);
+    else if (best_tq == 160) err = launch_tiled_tq<160>(select, p, best_smem, stream);
+    else err = launch_tiled_tq<192>(select, p, best_smem, stream);
     *rc = err == cudaSuccess ? ELO_OK : set_cuda_error(err, select ? "fused_conv_select_k (tiled) launch"
                                                                   : "fused_conv_random_k (tiled) launch");
     return 1;
