@@ -66,7 +66,9 @@ struct TiledParams {
     int vec_ok;          // every output pointer is 16-byte aligned
     unsigned magic_kt;   // ceil(2^32 / kt), ceil(2^32 / K): exact quotients for the writer's ranges
     unsigned magic_k;
+    int pitch;           // row pitch of the staged tile in cells (TQ + kW)
     int walk[MAX_WALK];  // select-K: window cells centre-out, (dh << 16) | (dw & 0xffff)
+    int walk_to[MAX_WALK];  // ... and their byte offsets in the staged tile, (row * pitch + col) * 16
 };
 
 struct TileGeom {
@@ -196,7 +198,7 @@ __global__ void __launch_bounds__(TQ, (KR <= 17 ? 896 / TQ : 512 / TQ)) fused_co
                 const long long th = (long long)hmax - hmin + g.kH, tw = (long long)rmax - rmin + g.kW;
                 // one wrap must be enough for every window cell (the reference wraps once, :88-96)
                 const bool wrap_ok = hw2 <= g.w2;
-                if (ok && bmin == bmax && wrap_ok && th * tw <= p.tile_cap) {
+                if (ok && bmin == bmax && wrap_ok && tw <= p.pitch && th * p.pitch <= p.tile_cap) {
                     tg.staged = 1; tg.th = (int)th; tg.tw = (int)tw; tg.hmin = hmin; tg.rmin = rmin;
                     tg.row0 = hmin - hh2; tg.col0 = cwref + rmin - hw2;
                 }
@@ -209,7 +211,9 @@ __global__ void __launch_bounds__(TQ, (KR <= 17 ? 896 / TQ : 512 / TQ)) fused_co
     }
     const TileGeom tg = *reinterpret_cast<const TileGeom*>(s_misc + 4);
     const bool staged = tg.staged == 1;
-    const int tw = tg.tw;
+    const int pitch = p.pitch;          // tile row pitch in cells: fixed per launch, so the walk's tile offsets
+                                        // are launch constants (kernel parameters -> uniform registers)
+    bool tied = false;                  // select-K: this query goes to the exact replay at the end
 
     if (tg.staged >= 0) {
         // ---- stage the tile: (x, y, z, 1 if the pixel is empty) ---------------------------------------------
@@ -218,7 +222,7 @@ __global__ void __launch_bounds__(TQ, (KR <= 17 ? 896 / TQ : 512 / TQ)) fused_co
             float4* t4 = reinterpret_cast<float4*>(tile);
             int c0 = tg.col0 % g.w2;
             if (c0 < 0) c0 += g.w2;
-            for (int c = tid; c < tw; c += TQ) {
+            for (int c = tid; c < tg.tw; c += TQ) {
                 const int gc = (c0 + c) % g.w2;
                 for (int r = 0; r < tg.th; ++r) {
                     const int gr = tg.row0 + r;
@@ -228,32 +232,32 @@ __global__ void __launch_bounds__(TQ, (KR <= 17 ? 896 / TQ : 512 / TQ)) fused_co
                         x = __ldg(s); y = __ldg(s + 1); z = __ldg(s + 2);
                     }
                     // empty pixel (reference :98-104); FSETP.GTU there: a NaN pixel counts as a point
-                    t4[r * tw + c] = make_float4(x, y, z, sq3(x, y, z) <= 1e-10f ? 1.0f : 0.0f);
+                    t4[r * pitch + c] = make_float4(x, y, z, sq3(x, y, z) <= 1e-10f ? 1.0f : 0.0f);
                 }
             }
         }
         // ---- walk tables ----------------------------------------------------------------------------------
         for (int j = tid; j < kt; j += TQ) {
-            int r, cc;
+            int pk, to;
             if (SELECT) {
-                const int pk = p.walk[j];
-                r = (pk >> 16) + hh2; cc = (int)(short)(pk & 0xffff) + hw2;
+                pk = p.walk[j]; to = p.walk_to[j];
             } else {
                 const int pp = __ldg(p.random_hw + j);
-                r = pp / g.kW; cc = pp - r * g.kW;
+                const int r = pp / g.kW, cc = pp - r * g.kW;
+                pk = ((r - hh2) << 16) | ((cc - hw2) & 0xffff);
+                to = (r * pitch + cc) * 16;
             }
-            walk_pk[j] = ((r - hh2) << 16) | ((cc - hw2) & 0xffff);
-            walk_to[j] = (r * tw + cc) * 16;
+            walk_pk[j] = pk;
+            walk_to[j] = to;
         }
         __syncthreads();
 
         // ---- the walk -----------------------------------------------------------------------------------
         const float* g2 = p.xyz2 + (size_t)b * g.h2 * g.w2 * 3;
         const unsigned char* tb = tile;
-        if (staged && cvalid) tb += ((ch - tg.hmin) * tw + (rel - tg.rmin)) * 16;
+        if (staged && cvalid) tb += ((ch - tg.hmin) * pitch + (rel - tg.rmin)) * 16;
         const float d2l = cvalid ? g.d2max : -1.0f;       // an invalid centre accepts nothing
         int nvalid = 0, nsel = 0;
-        float ninv = 0.f, nrej = 0.f;     // staged walk: empty / rejected cells, counted on the FP32 pipe
         auto cell_of = [&](int j) {
             const int pk = walk_pk[j];
             return pack_hw(ch + (pk >> 16), wrap_once(cw + (int)(short)(pk & 0xffff), g.w2));
@@ -262,30 +266,42 @@ __global__ void __launch_bounds__(TQ, (KR <= 17 ? 896 / TQ : 512 / TQ)) fused_co
         // ST = std::true_type: the window cells come from the staged tile; false_type: straight from the grid
         auto walk = [&](auto ST) {
             constexpr bool STG = decltype(ST)::value;
-            // cell j of the walk (tile offset `to` when staged) -> accepted?, distance; counts the valid cells
-            auto eval = [&](int j, int to, bool& acc, float& d) {
-                if constexpr (STG) {
-                    const float4 c = *reinterpret_cast<const float4*>(tb + to);
-                    ninv += c.w;
-                    d = fmaxf(sq3(__fsub_rn(xc, c.x), __fsub_rn(yc, c.y), __fsub_rn(zc, c.z)), 1e-10f);
-                    const float de = __fmaf_rn(c.w, 1e30f, d);    // + 0 for a point, + 1e30 for an empty pixel
-                    acc = !(de > d2l);
-                    if constexpr (SELECT) nrej += de > d2l ? 1.0f : 0.0f;
-                } else {
-                    const int pk = walk_pk[j];
-                    const int hh = ch + (pk >> 16);
-                    const int ww = wrap_once(cw + (int)(short)(pk & 0xffff), g.w2);
-                    const bool inb = hh >= 0 && hh < g.h2 && ww >= 0 && ww < g.w2;
-                    float xq = 0.f, yq = 0.f, zq = 0.f;
-                    if (inb && cvalid) {
-                        const float* s = g2 + ((size_t)hh * g.w2 + ww) * 3;
-                        xq = __ldg(s); yq = __ldg(s + 1); zq = __ldg(s + 2);
-                    }
-                    const bool valid = cvalid && inb && !(sq3(xq, yq, zq) <= 1e-10f);
-                    nvalid += valid;
-                    d = fmaxf(sq3(__fsub_rn(xc, xq), __fsub_rn(yc, yq), __fsub_rn(zc, zq)), 1e-10f);
-                    acc = valid && !(d > g.d2max);
+            float ninv = 0.f;             // staged walk: empty cells, counted on the FP32 pipe
+            int nrej = 0;                 // ... and cells that are empty or out of range
+            // direct path: cell j of the walk -> accepted?, distance; counts the valid cells
+            auto eval_direct = [&](int j, bool& acc, float& d) {
+                const int pk = walk_pk[j];
+                const int hh = ch + (pk >> 16);
+                const int ww = wrap_once(cw + (int)(short)(pk & 0xffff), g.w2);
+                const bool inb = hh >= 0 && hh < g.h2 && ww >= 0 && ww < g.w2;
+                float xq = 0.f, yq = 0.f, zq = 0.f;
+                if (inb && cvalid) {
+                    const float* s = g2 + ((size_t)hh * g.w2 + ww) * 3;
+                    xq = __ldg(s); yq = __ldg(s + 1); zq = __ldg(s + 2);
                 }
+                const bool valid = cvalid && inb && !(sq3(xq, yq, zq) <= 1e-10f);
+                nvalid += valid;
+                d = fmaxf(sq3(__fsub_rn(xc, xq), __fsub_rn(yc, yq), __fsub_rn(zc, zq)), 1e-10f);
+                acc = valid && !(d > g.d2max);
+            };
+            // staged path: the cell is already in registers
+            auto eval_cell = [&](const float4& c, bool& acc, float& d) {
+                ninv += c.w;
+                d = fmaxf(sq3(__fsub_rn(xc, c.x), __fsub_rn(yc, c.y), __fsub_rn(zc, c.z)), 1e-10f);
+                acc = !(__fmaf_rn(c.w, 1e30f, d) > d2l);      // + 0 for a point, + 1e30 for an empty pixel
+            };
+            // exact distance of walk cell j again (near-tie fix-up)
+            auto exact_d = [&](int j) {
+                bool acc; float d;
+                if constexpr (STG) {
+                    const float4 c = *reinterpret_cast<const float4*>(tb + walk_to[j]);
+                    d = fmaxf(sq3(__fsub_rn(xc, c.x), __fsub_rn(yc, c.y), __fsub_rn(zc, c.z)), 1e-10f);
+                } else {
+                    const int keep = nvalid;
+                    eval_direct(j, acc, d);
+                    nvalid = keep;
+                }
+                return d;
             };
 
             if constexpr (SELECT) {
@@ -293,29 +309,17 @@ __global__ void __launch_bounds__(TQ, (KR <= 17 ? 896 / TQ : 512 / TQ)) fused_co
 #pragma unroll
                 for (int i = 0; i < KR; ++i) a[i] = KEY_NONE;
                 const unsigned jmask = (1u << p.jbits) - 1u, nmask = ~jmask;     // jbits >= 4: QG positions fit
-                unsigned thr = KEY_NONE;
+                unsigned thr = 0xffffffffu;
                 unsigned* const qbase = queue + tid;
                 unsigned* qp = qbase;
                 // The key pushed by the filter carries only the position inside the group (a compile-time
                 // constant in the unrolled loop); the group base is OR-ed in when the queue is drained.  The
-                // filter may therefore mis-order a candidate against the current last key only when their
-                // distance bits are equal, which can change nothing but WHICH of two equal-distance keys sits
-                // in the last place -- and that is never output nor does it alter the near-tie test.
-                // `c` = the staged cell (ignored on the direct path, which loads inside eval_direct)
-                auto visit = [&](int jj, int j, const float4& c) {
-                    bool acc; float d;
-                    if constexpr (STG) {
-                        ninv += c.w;
-                        d = fmaxf(sq3(__fsub_rn(xc, c.x), __fsub_rn(yc, c.y), __fsub_rn(zc, c.z)), 1e-10f);
-                        const float de = __fmaf_rn(c.w, 1e30f, d);    // + 0 for a point, + 1e30 for an empty pixel
-                        acc = !(de > d2l);
-                        nrej += de > d2l ? 1.0f : 0.0f;
-                    } else {
-                        eval(j, 0, acc, d);
-                        nsel += acc;
-                    }
+                // filter lets every key through whose distance bits are <= those of the current last key, so
+                // the array always holds the KR smallest (distance bits, position) keys exactly.
+                auto push = [&](int jj, bool acc, float d) {
                     const unsigned key = (__float_as_uint(d) & nmask) | (unsigned)jj;
-                    if (acc && key < thr) { *qp = key; qp += TQ; }
+                    if (acc && key <= thr) { *qp = key; qp += TQ; }
+                    if constexpr (STG) { if (!acc) ++nrej; } else { nsel += acc; }
                 };
                 for (int jb = 0; jb < kt; jb += QG) {
                     if (jb + QG <= kt) {
@@ -323,25 +327,31 @@ __global__ void __launch_bounds__(TQ, (KR <= 17 ? 896 / TQ : 512 / TQ)) fused_co
                         // would otherwise have to keep them behind (shared memory may alias)
 #pragma unroll
                         for (int j8 = 0; j8 < QG; j8 += LB) {
-                            float4 c[LB];
                             if constexpr (STG) {
+                                float4 c[LB];
 #pragma unroll
-                                for (int i = 0; i < LB; i += 4) {
-                                    const int4 to = *reinterpret_cast<const int4*>(walk_to + jb + j8 + i);
-                                    c[i] = *reinterpret_cast<const float4*>(tb + to.x);
-                                    c[i + 1] = *reinterpret_cast<const float4*>(tb + to.y);
-                                    c[i + 2] = *reinterpret_cast<const float4*>(tb + to.z);
-                                    c[i + 3] = *reinterpret_cast<const float4*>(tb + to.w);
+                                for (int i = 0; i < LB; ++i) c[i] = *reinterpret_cast<const float4*>(tb + p.walk_to[jb + j8 + i]);
+#pragma unroll
+                                for (int i = 0; i < LB; ++i) {
+                                    bool acc; float d;
+                                    eval_cell(c[i], acc, d);
+                                    push(j8 + i, acc, d);
+                                }
+                            } else {
+#pragma unroll
+                                for (int i = 0; i < LB; ++i) {
+                                    bool acc; float d;
+                                    eval_direct(jb + j8 + i, acc, d);
+                                    push(j8 + i, acc, d);
                                 }
                             }
-#pragma unroll
-                            for (int i = 0; i < LB; ++i) visit(j8 + i, jb + j8 + i, c[i]);
                         }
                     } else {
                         for (int j = jb; j < kt; ++j) {
-                            float4 c = make_float4(0.f, 0.f, 0.f, 0.f);
-                            if constexpr (STG) c = *reinterpret_cast<const float4*>(tb + walk_to[j]);
-                            visit(j - jb, j, c);
+                            bool acc; float d;
+                            if constexpr (STG) eval_cell(*reinterpret_cast<const float4*>(tb + walk_to[j]), acc, d);
+                            else eval_direct(j, acc, d);
+                            push(j - jb, acc, d);
                         }
                     }
                     // drain: one insertion per queued key of the slowest lane
@@ -352,27 +362,39 @@ __global__ void __launch_bounds__(TQ, (KR <= 17 ? 896 / TQ : 512 / TQ)) fused_co
                         chain_insert<KR>(a, x);
                     }
                     qp = qbase;
-                    thr = a[KR - 1];
+                    thr = a[KR - 1] | jmask;
                 }
-                if constexpr (STG) nsel = kt - (int)nrej;
-                // near-ties among the K nearest (and against the first one left out) -> exact replay
+                if constexpr (STG) { nsel = kt - nrej; nvalid = kt - (int)ninv; }
+                if (!cvalid) { nsel = 0; nvalid = 0; }
+                // Near-ties: adjacent keys whose distance bits agree.  An isolated pair inside the K nearest is
+                // put in order by its exact distances; an exact tie, a run of three, or a pair that straddles
+                // the K-th place (a cell that fell out of the array could belong between them) goes to the
+                // exact replay.
                 const int nw = min(nsel, K);
-                bool tie = false;
+                bool prev_eq = false;
 #pragma unroll
-                for (int i = 0; i + 1 < KR; ++i)
-                    if (i < K && i + 1 < nsel && ((a[i] ^ a[i + 1]) & ~jmask) == 0u) tie = true;
-                int first = 0;
-                if (!tie) {
-#pragma unroll
-                    for (int s = 0; s < KR - 1; ++s)
-                        if (s < nw) {
-                            const int c = cell_of((int)(a[s] & jmask));
-                            sel[s * TQ + tid] = c;
-                            if (s == 0) first = c;
+                for (int i = 0; i + 1 < KR; ++i) {
+                    const bool eq = i < K && i + 1 < nsel && ((a[i] ^ a[i + 1]) & nmask) == 0u;
+                    if (eq) {
+                        if (prev_eq || i + 1 >= K) {
+                            tied = true;
+                        } else {
+                            const float d0 = exact_d((int)(a[i] & jmask)), d1 = exact_d((int)(a[i + 1] & jmask));
+                            if (d0 == d1) tied = true;
+                            else if (d1 < d0) { const unsigned t = a[i]; a[i] = a[i + 1]; a[i + 1] = t; }
                         }
-                } else {
-                    s_ties[atomicAdd(&s_misc[0], 1)] = tid;
+                    }
+                    prev_eq = eq;
                 }
+                int first = 0;
+#pragma unroll
+                for (int s = 0; s < KR - 1; ++s)
+                    if (s < nw) {
+                        const int c = cell_of((int)(a[s] & jmask));
+                        sel[s * TQ + tid] = c;
+                        if (s == 0) first = c;
+                    }
+                if (tied) s_ties[atomicAdd(&s_misc[0], 1)] = tid;
                 s_nwr[tid] = nw;
                 s_first[tid] = first;
             } else {
@@ -381,7 +403,8 @@ __global__ void __launch_bounds__(TQ, (KR <= 17 ? 896 / TQ : 512 / TQ)) fused_co
                 for (int j = 0; j < kt; ++j) {
                     if (!done) {
                         bool acc; float d;
-                        eval(j, walk_to[j], acc, d);
+                        if constexpr (STG) eval_cell(*reinterpret_cast<const float4*>(tb + walk_to[j]), acc, d);
+                        else eval_direct(j, acc, d);
                         if (acc) {
                             const int c = cell_of(j);
                             if (nsel == 0) first = c;
@@ -398,60 +421,31 @@ __global__ void __launch_bounds__(TQ, (KR <= 17 ? 896 / TQ : 512 / TQ)) fused_co
                 if constexpr (STG) {
                     if (!done) nvalid = kt - (int)ninv;
                 }
+                if (!cvalid) { nsel = 0; nvalid = 0; }
                 s_nwr[tid] = nsel;
                 s_first[tid] = first;
             }
-            if constexpr (STG && SELECT) nvalid = kt - (int)ninv;
         };
         if (staged) walk(std::true_type{});
         else walk(std::false_type{});
-        if (!cvalid) { nvalid = 0; nsel = 0; }
         s_nv[tid] = (float)nvalid;
         s_ns[tid] = (float)nsel;
         // select-K duplicates entry 0 even when nothing was in range (mask 1, index (b,0,0)); random-K only
         // once a first neighbour was accepted (reference select :180-192, random :126-138)
         s_bcopy[tid] = (b << 1) | ((cvalid && g.flag_copy == 1 && (SELECT || nsel > 0)) ? 1 : 0);
-        __syncthreads();
-
-        // ---- exact replay of the tied queries (warp-cooperative, reference scan order) ---------------------
-        if (SELECT) {
-            const int nties = s_misc[0];
-            if (nties > 0) {
-                // the tile is no longer needed: scan-order offsets + per-warp scratch live there now
-                int2* off_scan = reinterpret_cast<int2*>(tile);
-                float* dist = reinterpret_cast<float*>(tile + (size_t)kt * 8) + (size_t)warp * kt;
-                int* hwv = reinterpret_cast<int*>(tile + (size_t)kt * 8 + (size_t)TW * kt * 4) + (size_t)warp * kt;
-                build_offsets(off_scan, p.random_hw, kt, g.kH, g.kW, TQ);
-                __syncthreads();
-                for (int t = warp; t < nties; t += TW) {
-                    const int qt = s_ties[t];
-                    const long long gq = q0 + qt;
-                    const int bq = (int)(gq / p.N);
-                    const int2 hwq = __ldg(reinterpret_cast<const int2*>(p.idx_n2) + gq);
-                    const float* c = p.xyz1 + ((size_t)bq * p.H * p.W + (size_t)hwq.x * p.W + hwq.y) * 3;
-                    const float* g2q = p.xyz2 + (size_t)bq * g.h2 * g.w2 * 3;
-                    auto emit = [&](int slot, int hh, int ww) { sel[slot * TQ + qt] = pack_hw(hh, ww); };
-                    int written = 0;
-                    const SearchCounts sc = search_select_k(g2q, off_scan, g, hwq.x / g.stride_h, hwq.y / g.stride_w, __ldg(c),
-                                                            __ldg(c + 1), __ldg(c + 2), dist, hwv, &written, emit);
-                    __syncwarp();
-                    if (lane == 0) { s_nwr[qt] = written; s_first[qt] = sc.first; }
-                    __syncwarp();
-                }
-                __syncthreads();
-            }
-        }
     } else {
         s_nv[tid] = 0.f; s_ns[tid] = 0.f; s_nwr[tid] = 0; s_first[tid] = 0; s_bcopy[tid] = b << 1;
-        __syncthreads();
     }
+    __syncwarp();
 
-    // ---- write the CTA's TQ rows of every output ------------------------------------------------------------
-    const int nq = (int)min((long long)TQ, p.total - q0);
-    // slot `sl` of the CTA (query sl / K, slot sl % K) -> (b, hh, ww) and mask
+    // ---- each warp writes the 32 rows of its own queries: no CTA-wide barrier between walk and write, so the
+    //      warps of an SM drift apart and one warp's stores overlap another's arithmetic ---------------------------
+    const int r_lo = warp * 32;                                           // first CTA-local row of this warp
+    const int nrows = (int)max(0ll, min(32ll, p.total - q0 - r_lo));
+    // slot `sl` of the warp (row sl / K, slot sl % K) -> (b, hh, ww) and mask
     auto slot_value = [&](unsigned sl, int& vb, int& vh, int& vw, float& vm) {
         unsigned s;
-        const unsigned r = udiv_magic(sl, p.magic_k, (unsigned)K, s);
+        const unsigned r = r_lo + udiv_magic(sl, p.magic_k, (unsigned)K, s);
         const int bc = s_bcopy[r];
         int pk = 0;
         bool on = false;
@@ -459,12 +453,12 @@ __global__ void __launch_bounds__(TQ, (KR <= 17 ? 896 / TQ : 512 / TQ)) fused_co
         else if (bc & 1) { pk = s_first[r]; on = true; }
         vb = on ? (bc >> 1) : 0; vh = pk >> 16; vw = pk & 0xffff; vm = on ? 1.0f : 0.0f;
     };
-    {
-        int* o_idx = p.out_idx + q0 * K * 3;
-        float* o_mask = p.out_mask + q0 * K;
-        const unsigned nslots = (unsigned)nq * K;
+    if (nrows > 0) {
+        int* o_idx = p.out_idx + (q0 + r_lo) * K * 3;
+        float* o_mask = p.out_mask + (q0 + r_lo) * K;
+        const unsigned nslots = (unsigned)nrows * K;
         const unsigned ngroups = p.vec_ok ? nslots / 4 : 0;
-        for (unsigned gi = tid; gi < ngroups; gi += TQ) {
+        for (unsigned gi = lane; gi < ngroups; gi += 32) {
             int v[12];
             float m[4];
 #pragma unroll
@@ -475,22 +469,22 @@ __global__ void __launch_bounds__(TQ, (KR <= 17 ? 896 / TQ : 512 / TQ)) fused_co
             o[2] = make_int4(v[8], v[9], v[10], v[11]);
             reinterpret_cast<float4*>(o_mask)[gi] = make_float4(m[0], m[1], m[2], m[3]);
         }
-        for (unsigned sl = ngroups * 4 + tid; sl < nslots; sl += TQ) {
+        for (unsigned sl = ngroups * 4 + lane; sl < nslots; sl += 32) {
             int vb, vh, vw; float vm;
             slot_value(sl, vb, vh, vw, vm);
             o_idx[(size_t)sl * 3] = vb; o_idx[(size_t)sl * 3 + 1] = vh; o_idx[(size_t)sl * 3 + 2] = vw;
             o_mask[sl] = vm;
         }
     }
-    if (p.out_valid != nullptr || p.out_vdis != nullptr) {
+    if (nrows > 0 && (p.out_valid != nullptr || p.out_vdis != nullptr)) {
         // valid_idx / valid_in_dis_idx rows are a run of ones followed by zeros.  Four rows are kt float4s,
-        // 16-byte aligned; a thread keeps the same float4 column f for every block of four rows, so which
+        // 16-byte aligned; a lane keeps the same float4 column f for every block of four rows, so which
         // rows its four elements belong to (at most two when kt >= 4) and their positions are loop-invariant,
         // and an element is saturate(count - position): one FADD.SAT on the FP32 pipe per element and row.
-        float* o_valid = p.out_valid ? p.out_valid + q0 * kt : nullptr;
-        float* o_vdis = p.out_vdis ? p.out_vdis + q0 * kt : nullptr;
-        const int nblk = (p.vec_ok && kt >= 4) ? nq / 4 : 0;
-        for (int f = tid; f < kt && nblk > 0; f += TQ) {
+        float* o_valid = p.out_valid ? p.out_valid + (q0 + r_lo) * kt : nullptr;
+        float* o_vdis = p.out_vdis ? p.out_vdis + (q0 + r_lo) * kt : nullptr;
+        const int nblk = (p.vec_ok && kt >= 4) ? nrows / 4 : 0;
+        for (int f = lane; f < kt && nblk > 0; f += 32) {
             unsigned pos0, pos3;
             const int r0 = (int)udiv_magic(4u * f, p.magic_kt, (unsigned)kt, pos0);
             const int r3 = (int)udiv_magic(4u * f + 3u, p.magic_kt, (unsigned)kt, pos3);
@@ -504,8 +498,8 @@ __global__ void __launch_bounds__(TQ, (KR <= 17 ? 896 / TQ : 512 / TQ)) fused_co
             }
             float4* ov = o_valid ? reinterpret_cast<float4*>(o_valid) + f : nullptr;
             float4* od = o_vdis ? reinterpret_cast<float4*>(o_vdis) + f : nullptr;
-            const float* nva = s_nv + r0; const float* nvb = s_nv + r3;
-            const float* nsa = s_ns + r0; const float* nsb = s_ns + r3;
+            const float* nva = s_nv + r_lo + r0; const float* nvb = s_nv + r_lo + r3;
+            const float* nsa = s_ns + r_lo + r0; const float* nsb = s_ns + r_lo + r3;
 #pragma unroll 2
             for (int blk = 0; blk < nblk; ++blk) {
                 const float va = nva[4 * blk], vb = nvb[4 * blk], da = nsa[4 * blk], db = nsb[4 * blk];
@@ -519,12 +513,52 @@ __global__ void __launch_bounds__(TQ, (KR <= 17 ? 896 / TQ : 512 / TQ)) fused_co
                 if (od) od[(size_t)blk * kt] = make_float4(d4[0], d4[1], d4[2], d4[3]);
             }
         }
-        const unsigned nel = (unsigned)nq * kt;
-        for (unsigned e = (unsigned)nblk * 4u * kt + tid; e < nel; e += TQ) {
+        const unsigned nel = (unsigned)nrows * kt;
+        for (unsigned e = (unsigned)nblk * 4u * kt + lane; e < nel; e += 32) {
             unsigned pos;
-            const unsigned r = udiv_magic(e, p.magic_kt, (unsigned)kt, pos);
+            const unsigned r = r_lo + udiv_magic(e, p.magic_kt, (unsigned)kt, pos);
             if (o_valid) o_valid[e] = (float)pos < s_nv[r] ? 1.0f : 0.0f;
             if (o_vdis) o_vdis[e] = (float)pos < s_ns[r] ? 1.0f : 0.0f;
+        }
+    }
+
+    // ---- exact replay of the tied queries (warp-cooperative, reference scan order), then their rows again ---------
+    if (SELECT) {
+        __syncthreads();                        // every walk is over: tie list complete, tile free
+        const int nties = s_misc[0];
+        if (nties > 0) {
+            int2* off_scan = reinterpret_cast<int2*>(tile);
+            float* dist = reinterpret_cast<float*>(tile + (size_t)kt * 8) + (size_t)warp * kt;
+            int* hwv = reinterpret_cast<int*>(tile + (size_t)kt * 8 + (size_t)TW * kt * 4) + (size_t)warp * kt;
+            build_offsets(off_scan, p.random_hw, kt, g.kH, g.kW, TQ);
+            __syncthreads();
+            for (int t = warp; t < nties; t += TW) {
+                const int qt = s_ties[t];
+                const long long gq = q0 + qt;
+                const int bq = (int)(gq / p.N);
+                const int2 hwq = __ldg(reinterpret_cast<const int2*>(p.idx_n2) + gq);
+                const float* c = p.xyz1 + ((size_t)bq * p.H * p.W + (size_t)hwq.x * p.W + hwq.y) * 3;
+                const float* g2q = p.xyz2 + (size_t)bq * g.h2 * g.w2 * 3;
+                int* o_idx = p.out_idx + gq * K * 3;
+                float* o_mask = p.out_mask + gq * K;
+                auto emit = [&](int slot, int hh, int ww) {
+                    o_idx[slot * 3] = bq; o_idx[slot * 3 + 1] = hh; o_idx[slot * 3 + 2] = ww;
+                    o_mask[slot] = 1.0f;
+                };
+                int written = 0;
+                const SearchCounts sc = search_select_k(g2q, off_scan, g, hwq.x / g.stride_h, hwq.y / g.stride_w, __ldg(c),
+                                                        __ldg(c + 1), __ldg(c + 2), dist, hwv, &written, emit);
+                __syncwarp();
+                // slots the replay did not emit: zero, or the duplicate of entry 0 (flag_copy)
+                const bool copy = g.flag_copy == 1;
+                for (int k = written + lane; k < K; k += 32) {
+                    o_idx[k * 3] = copy ? bq : 0;
+                    o_idx[k * 3 + 1] = copy ? sc.first >> 16 : 0;
+                    o_idx[k * 3 + 2] = copy ? sc.first & 0xffff : 0;
+                    o_mask[k] = copy ? 1.0f : 0.0f;
+                }
+                __syncwarp();
+            }
         }
     }
 }
@@ -562,7 +596,7 @@ static size_t tiled_smem(const Window& g, bool select, int tq, int* tile_cap, in
 {
     auto up = [](size_t b) { return (b + 15) & ~size_t(15); };
     // raster-order queries: tq centres on one or two rows (fewer columns when the window centre is strided)
-    *tile_cap = (g.kH + 1) * (tq + g.kW);
+    *tile_cap = (g.kH + 1) * (tq + g.kW);      // rows x pitch
     size_t tb = (size_t)*tile_cap * 16;
     if (select) tb = std::max(tb, (size_t)g.kt * 8 + 2 * (size_t)(tq / 32) * g.kt * 4);   // replay scratch
     *tile_bytes = (int)up(tb);
@@ -629,6 +663,14 @@ int launch_index_tiled(bool select, int B, int H, int W, int N, const Window& g,
     }
     if (best_tq == 0) return 0;
     tiled_smem(g, select, best_tq, &p.tile_cap, &p.tile_bytes);
+    p.pitch = best_tq + g.kW;
+    if (select) {
+        const int hh2 = g.kH / 2, hw2 = g.kW / 2;
+        for (int j = 0; j < g.kt; ++j) {
+            const int dh = p.walk[j] >> 16, dw = (int)(short)(p.walk[j] & 0xffff);
+            p.walk_to[j] = ((dh + hh2) * p.pitch + (dw + hw2)) * 16;
+        }
+    }
 
     cudaError_t err;
     if (best_tq == 128) err = launch_tiled_tq<128>(select, p, best_smem, stream);
