@@ -27,6 +27,7 @@
 // grid through the read-only cache instead of the staged tile; results are identical.
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <math.h>
 #include <stdlib.h>
 
 #include <algorithm>
@@ -67,6 +68,7 @@ struct TiledParams {
     unsigned magic_kt;   // ceil(2^32 / kt), ceil(2^32 / K): exact quotients for the writer's ranges
     unsigned magic_k;
     int pitch;           // row pitch of the staged tile in cells (TQ + kW)
+    float near_bound;    // sqrt(distance^2 / 12.5): coordinates within it are all mutually in range
     int walk[MAX_WALK];  // select-K: window cells centre-out, (dh << 16) | (dw & 0xffff)
     int walk_to[MAX_WALK];  // ... and their byte offsets in the staged tile, (row * pitch + col) * 16
 };
@@ -215,8 +217,96 @@ __global__ void __launch_bounds__(TQ, (KR <= 17 ? 896 / TQ : 512 / TQ)) fused_co
                                         // are launch constants (kernel parameters -> uniform registers)
     bool tied = false;                  // select-K: this query goes to the exact replay at the end
 
+    // ---- row writers.  Each warp writes the 32 rows of its own queries: no CTA-wide barrier between walk and
+    //      write, so the warps of an SM drift apart and one warp's stores overlap another's arithmetic. -----------
+    const int r_lo = warp * 32;                                           // first CTA-local row of this warp
+    const int nrows = (int)max(0ll, min(32ll, p.total - q0 - r_lo));
+    // valid_idx / valid_in_dis_idx rows are a run of ones followed by zeros.  Four rows are kt float4s,
+    // 16-byte aligned; a lane keeps the same float4 column f for every block of four rows, so which
+    // rows its four elements belong to (at most two when kt >= 4) and their positions are loop-invariant,
+    // and an element is saturate(count - position): one FADD.SAT on the FP32 pipe per element and row.
+    float* const o_valid = (p.out_valid && nrows > 0) ? p.out_valid + (q0 + r_lo) * kt : nullptr;
+    float* const o_vdis = (p.out_vdis && nrows > 0) ? p.out_vdis + (q0 + r_lo) * kt : nullptr;
+    const bool want_rows = o_valid != nullptr || o_vdis != nullptr;
+    const int nblk = (p.vec_ok && kt >= 4) ? nrows / 4 : 0;
+    const int nfi = (nblk > 0 && want_rows) ? (kt + 31) / 32 : 0;         // column chunks of 32 float4s
+    // column chunk fi: float4 column f = 32 fi + lane of every block of four rows.  Two warp-uniform
+    // shortcuts: no lane of the chunk straddles two rows (one term per element instead of two), and
+    // valid_in_dis_idx == valid_idx for all 32 queries (`same`: computed once, stored twice).
+    auto valid_rows_chunk = [&](int fi, bool same) {
+        const int f = 32 * fi + lane;
+        const bool on = f < kt;
+        unsigned pos0 = 0, pos3 = 0;
+        int r0 = 0, r3 = 0;
+        if (on) {
+            r0 = (int)udiv_magic(4u * f, p.magic_kt, (unsigned)kt, pos0);
+            r3 = (int)udiv_magic(4u * f + 3u, p.magic_kt, (unsigned)kt, pos3);
+        }
+        const bool straddle = __any_sync(FULL_MASK, on && r0 != r3);
+        if (!on) return;
+        // element i sits in row r0 at pos0 + i while that is < kt, else in row r3 at pos0 + i - kt
+        float pa[4], pb[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const bool lo = (int)pos0 + i < kt;
+            pa[i] = lo ? (float)((int)pos0 + i) : 1e9f;
+            pb[i] = lo ? 1e9f : (float)((int)pos0 + i - kt);
+        }
+        float4* ov = o_valid ? reinterpret_cast<float4*>(o_valid) + f : nullptr;
+        float4* od = o_vdis ? reinterpret_cast<float4*>(o_vdis) + f : nullptr;
+        const float* nva = s_nv + r_lo + r0; const float* nvb = s_nv + r_lo + r3;
+        const float* nsa = s_ns + r_lo + r0; const float* nsb = s_ns + r_lo + r3;
+        auto body = [&](auto STR, auto SAME) {
+            constexpr bool two = decltype(STR)::value, one_array = decltype(SAME)::value;
+#pragma unroll 4
+            for (int blk = 0; blk < nblk; ++blk) {
+                float a4[4], d4[4];
+                const float va = nva[4 * blk];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) a4[i] = __saturatef(va - pa[i]);
+                if constexpr (two) {
+                    const float vb = nvb[4 * blk];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) a4[i] += __saturatef(vb - pb[i]);
+                }
+                if constexpr (one_array) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) d4[i] = a4[i];
+                } else {
+                    const float da = nsa[4 * blk];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) d4[i] = __saturatef(da - pa[i]);
+                    if constexpr (two) {
+                        const float db = nsb[4 * blk];
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) d4[i] += __saturatef(db - pb[i]);
+                    }
+                }
+                if (ov) __stcs(ov + (size_t)blk * kt, make_float4(a4[0], a4[1], a4[2], a4[3]));
+                if (od) __stcs(od + (size_t)blk * kt, make_float4(d4[0], d4[1], d4[2], d4[3]));
+            }
+        };
+        if (straddle) { if (same) body(std::true_type{}, std::true_type{}); else body(std::true_type{}, std::false_type{}); }
+        else          { if (same) body(std::false_type{}, std::true_type{}); else body(std::false_type{}, std::false_type{}); }
+    };
+    // rows that do not fill a block of four (or unaligned outputs): element by element
+    auto valid_rows_tail = [&]() {
+        if (!want_rows) return;
+        const unsigned nel = (unsigned)nrows * kt;
+        for (unsigned e = (unsigned)nblk * 4u * kt + lane; e < nel; e += 32) {
+            unsigned pos;
+            const unsigned r = r_lo + udiv_magic(e, p.magic_kt, (unsigned)kt, pos);
+            if (o_valid) o_valid[e] = (float)pos < s_nv[r] ? 1.0f : 0.0f;
+            if (o_vdis) o_vdis[e] = (float)pos < s_ns[r] ? 1.0f : 0.0f;
+        }
+    };
+
     if (tg.staged >= 0) {
         // ---- stage the tile: (x, y, z, 1 if the pixel is empty) ---------------------------------------------
+        // `far`: not every coordinate is within near_bound = sqrt(distance^2 / 12.5) of the origin.  When none
+        // is, every point of the neighbourhood is within `distance` of every centre (|c - q|^2 <= 12 bound^2),
+        // so valid_in_dis_idx == valid_idx and the walk needs neither the range test nor its counter.
+        bool far = cvalid && !(fmaxf(fmaxf(fabsf(xc), fabsf(yc)), fabsf(zc)) <= p.near_bound);
         if (staged) {
             const float* g2 = p.xyz2 + (size_t)tg.b * g.h2 * g.w2 * 3;
             float4* t4 = reinterpret_cast<float4*>(tile);
@@ -233,9 +323,11 @@ __global__ void __launch_bounds__(TQ, (KR <= 17 ? 896 / TQ : 512 / TQ)) fused_co
                     }
                     // empty pixel (reference :98-104); FSETP.GTU there: a NaN pixel counts as a point
                     t4[r * pitch + c] = make_float4(x, y, z, sq3(x, y, z) <= 1e-10f ? 1.0f : 0.0f);
+                    far = far || !(fmaxf(fmaxf(fabsf(x), fabsf(y)), fabsf(z)) <= p.near_bound);
                 }
             }
         }
+        if (far) s_misc[2] = 1;          // some coordinate of the neighbourhood is large, infinite or NaN
         // ---- walk tables ----------------------------------------------------------------------------------
         for (int j = tid; j < kt; j += TQ) {
             int pk, to;
@@ -264,8 +356,10 @@ __global__ void __launch_bounds__(TQ, (KR <= 17 ? 896 / TQ : 512 / TQ)) fused_co
         };
 
         // ST = std::true_type: the window cells come from the staged tile; false_type: straight from the grid
-        auto walk = [&](auto ST) {
+        // NR = true_type (select-K on a staged tile only): every point is within range of every centre
+        auto walk = [&](auto ST, auto NR) {
             constexpr bool STG = decltype(ST)::value;
+            constexpr bool NEAR = decltype(NR)::value;
             float ninv = 0.f;             // staged walk: empty cells, counted on the FP32 pipe
             int nrej = 0;                 // ... and cells that are empty or out of range
             // direct path: cell j of the walk -> accepted?, distance; counts the valid cells
@@ -309,17 +403,31 @@ __global__ void __launch_bounds__(TQ, (KR <= 17 ? 896 / TQ : 512 / TQ)) fused_co
 #pragma unroll
                 for (int i = 0; i < KR; ++i) a[i] = KEY_NONE;
                 const unsigned jmask = (1u << p.jbits) - 1u, nmask = ~jmask;     // jbits >= 4: QG positions fit
-                unsigned thr = 0xffffffffu;
-                unsigned* const qbase = queue + tid;
-                unsigned* qp = qbase;
+                unsigned thr = NEAR ? (KEY_NONE | jmask) : 0xffffffffu;
+                const unsigned qbase = (unsigned)__cvta_generic_to_shared(queue + tid);
+                unsigned qp = qbase;
+                // centre of a query that must accept nothing (NEAR path): every distance overflows
+                const float xs = (NEAR && !cvalid) ? 3e38f : xc, ys = (NEAR && !cvalid) ? 3e38f : yc,
+                            zs = (NEAR && !cvalid) ? 3e38f : zc;
                 // The key pushed by the filter carries only the position inside the group (a compile-time
                 // constant in the unrolled loop); the group base is OR-ed in when the queue is drained.  The
                 // filter lets every key through whose distance bits are <= those of the current last key, so
                 // the array always holds the KR smallest (distance bits, position) keys exactly.
                 auto push = [&](int jj, bool acc, float d) {
                     const unsigned key = (__float_as_uint(d) & nmask) | (unsigned)jj;
-                    if (acc && key <= thr) { *qp = key; qp += TQ; }
-                    if constexpr (STG) { if (!acc) ++nrej; } else { nsel += acc; }
+                    if (acc && key <= thr) {
+                        asm volatile("st.shared.u32 [%0], %1;" ::"r"(qp), "r"(key) : "memory");
+                        qp += TQ * 4;
+                    }
+                    if constexpr (!NEAR) {
+                        if constexpr (STG) { if (!acc) ++nrej; } else { nsel += acc; }
+                    }
+                };
+                // NEAR: an empty pixel gets a key above every threshold, so the key test is the whole filter
+                auto eval_near = [&](const float4& c, float& d) {
+                    ninv += c.w;
+                    d = fmaxf(sq3(__fsub_rn(xs, c.x), __fsub_rn(ys, c.y), __fsub_rn(zs, c.z)), 1e-10f);
+                    return __fmaf_rn(c.w, 3e38f, d);
                 };
                 for (int jb = 0; jb < kt; jb += QG) {
                     if (jb + QG <= kt) {
@@ -333,8 +441,9 @@ __global__ void __launch_bounds__(TQ, (KR <= 17 ? 896 / TQ : 512 / TQ)) fused_co
                                 for (int i = 0; i < LB; ++i) c[i] = *reinterpret_cast<const float4*>(tb + p.walk_to[jb + j8 + i]);
 #pragma unroll
                                 for (int i = 0; i < LB; ++i) {
-                                    bool acc; float d;
-                                    eval_cell(c[i], acc, d);
+                                    bool acc = true; float d;
+                                    if constexpr (NEAR) { float dd; d = eval_near(c[i], dd); }
+                                    else eval_cell(c[i], acc, d);
                                     push(j8 + i, acc, d);
                                 }
                             } else {
@@ -348,23 +457,25 @@ __global__ void __launch_bounds__(TQ, (KR <= 17 ? 896 / TQ : 512 / TQ)) fused_co
                         }
                     } else {
                         for (int j = jb; j < kt; ++j) {
-                            bool acc; float d;
-                            if constexpr (STG) eval_cell(*reinterpret_cast<const float4*>(tb + walk_to[j]), acc, d);
+                            bool acc = true; float d;
+                            if constexpr (NEAR) { float dd; d = eval_near(*reinterpret_cast<const float4*>(tb + walk_to[j]), dd); }
+                            else if constexpr (STG) eval_cell(*reinterpret_cast<const float4*>(tb + walk_to[j]), acc, d);
                             else eval_direct(j, acc, d);
                             push(j - jb, acc, d);
                         }
                     }
                     // drain: one insertion per queued key of the slowest lane
-                    const int cnt = (int)(qp - qbase) / TQ;
+                    const int cnt = (int)(qp - qbase) / (TQ * 4);
                     const int n = __reduce_max_sync(FULL_MASK, cnt);
                     for (int t = 0; t < n; ++t) {
-                        const unsigned x = t < cnt ? (qbase[t * TQ] | (unsigned)jb) : 0xffffffffu;
+                        const unsigned x = t < cnt ? (queue[t * TQ + tid] | (unsigned)jb) : 0xffffffffu;
                         chain_insert<KR>(a, x);
                     }
                     qp = qbase;
                     thr = a[KR - 1] | jmask;
                 }
-                if constexpr (STG) { nsel = kt - nrej; nvalid = kt - (int)ninv; }
+                if constexpr (NEAR) { nvalid = cvalid ? kt - (int)ninv : 0; nsel = nvalid; }
+                if constexpr (STG && !NEAR) { nsel = kt - nrej; nvalid = kt - (int)ninv; }
                 if (!cvalid) { nsel = 0; nvalid = 0; }
                 // Near-ties: adjacent keys whose distance bits agree.  An isolated pair inside the K nearest is
                 // put in order by its exact distances; an exact tie, a run of three, or a pair that straddles
@@ -426,8 +537,10 @@ __global__ void __launch_bounds__(TQ, (KR <= 17 ? 896 / TQ : 512 / TQ)) fused_co
                 s_first[tid] = first;
             }
         };
-        if (staged) walk(std::true_type{});
-        else walk(std::false_type{});
+        const bool all_near = SELECT && staged && s_misc[2] == 0;
+        if (all_near) walk(std::true_type{}, std::true_type{});
+        else if (staged) walk(std::true_type{}, std::false_type{});
+        else walk(std::false_type{}, std::false_type{});
         s_nv[tid] = (float)nvalid;
         s_ns[tid] = (float)nsel;
         // select-K duplicates entry 0 even when nothing was in range (mask 1, index (b,0,0)); random-K only
@@ -438,10 +551,6 @@ __global__ void __launch_bounds__(TQ, (KR <= 17 ? 896 / TQ : 512 / TQ)) fused_co
     }
     __syncwarp();
 
-    // ---- each warp writes the 32 rows of its own queries: no CTA-wide barrier between walk and write, so the
-    //      warps of an SM drift apart and one warp's stores overlap another's arithmetic ---------------------------
-    const int r_lo = warp * 32;                                           // first CTA-local row of this warp
-    const int nrows = (int)max(0ll, min(32ll, p.total - q0 - r_lo));
     // slot `sl` of the warp (row sl / K, slot sl % K) -> (b, hh, ww) and mask
     auto slot_value = [&](unsigned sl, int& vb, int& vh, int& vw, float& vm) {
         unsigned s;
@@ -476,50 +585,10 @@ __global__ void __launch_bounds__(TQ, (KR <= 17 ? 896 / TQ : 512 / TQ)) fused_co
             o_mask[sl] = vm;
         }
     }
-    if (nrows > 0 && (p.out_valid != nullptr || p.out_vdis != nullptr)) {
-        // valid_idx / valid_in_dis_idx rows are a run of ones followed by zeros.  Four rows are kt float4s,
-        // 16-byte aligned; a lane keeps the same float4 column f for every block of four rows, so which
-        // rows its four elements belong to (at most two when kt >= 4) and their positions are loop-invariant,
-        // and an element is saturate(count - position): one FADD.SAT on the FP32 pipe per element and row.
-        float* o_valid = p.out_valid ? p.out_valid + (q0 + r_lo) * kt : nullptr;
-        float* o_vdis = p.out_vdis ? p.out_vdis + (q0 + r_lo) * kt : nullptr;
-        const int nblk = (p.vec_ok && kt >= 4) ? nrows / 4 : 0;
-        for (int f = lane; f < kt && nblk > 0; f += 32) {
-            unsigned pos0, pos3;
-            const int r0 = (int)udiv_magic(4u * f, p.magic_kt, (unsigned)kt, pos0);
-            const int r3 = (int)udiv_magic(4u * f + 3u, p.magic_kt, (unsigned)kt, pos3);
-            // element i sits in row r0 at pos0 + i while that is < kt, else in row r3 at pos0 + i - kt
-            float pa[4], pb[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const bool lo = (int)pos0 + i < kt;
-                pa[i] = lo ? (float)((int)pos0 + i) : 1e9f;
-                pb[i] = lo ? 1e9f : (float)((int)pos0 + i - kt);
-            }
-            float4* ov = o_valid ? reinterpret_cast<float4*>(o_valid) + f : nullptr;
-            float4* od = o_vdis ? reinterpret_cast<float4*>(o_vdis) + f : nullptr;
-            const float* nva = s_nv + r_lo + r0; const float* nvb = s_nv + r_lo + r3;
-            const float* nsa = s_ns + r_lo + r0; const float* nsb = s_ns + r_lo + r3;
-#pragma unroll 2
-            for (int blk = 0; blk < nblk; ++blk) {
-                const float va = nva[4 * blk], vb = nvb[4 * blk], da = nsa[4 * blk], db = nsb[4 * blk];
-                float a4[4], d4[4];
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    a4[i] = __saturatef(va - pa[i]) + __saturatef(vb - pb[i]);
-                    d4[i] = __saturatef(da - pa[i]) + __saturatef(db - pb[i]);
-                }
-                if (ov) ov[(size_t)blk * kt] = make_float4(a4[0], a4[1], a4[2], a4[3]);
-                if (od) od[(size_t)blk * kt] = make_float4(d4[0], d4[1], d4[2], d4[3]);
-            }
-        }
-        const unsigned nel = (unsigned)nrows * kt;
-        for (unsigned e = (unsigned)nblk * 4u * kt + lane; e < nel; e += 32) {
-            unsigned pos;
-            const unsigned r = r_lo + udiv_magic(e, p.magic_kt, (unsigned)kt, pos);
-            if (o_valid) o_valid[e] = (float)pos < s_nv[r] ? 1.0f : 0.0f;
-            if (o_vdis) o_vdis[e] = (float)pos < s_ns[r] ? 1.0f : 0.0f;
-        }
+    {
+        const bool same = __all_sync(FULL_MASK, s_nv[tid] == s_ns[tid]);
+        for (int fi = 0; fi < nfi; ++fi) valid_rows_chunk(fi, same);
+        valid_rows_tail();
     }
 
     // ---- exact replay of the tied queries (warp-cooperative, reference scan order), then their rows again ---------
@@ -664,6 +733,7 @@ int launch_index_tiled(bool select, int B, int H, int W, int N, const Window& g,
     if (best_tq == 0) return 0;
     tiled_smem(g, select, best_tq, &p.tile_cap, &p.tile_bytes);
     p.pitch = best_tq + g.kW;
+    p.near_bound = sqrtf(g.d2max / 12.5f);
     if (select) {
         const int hh2 = g.kH / 2, hw2 = g.kW / 2;
         for (int j = 0; j < g.kt; ++j) {
