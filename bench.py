@@ -166,30 +166,46 @@ def algorithmic_work(name, tag, B):
     return None, None
 
 
-def index_op_roofline(elo, dev, peaks, iters=10):
+def index_op_roofline(elo, dev, peaks, iters=20):
     """BASELINE.json configs[0]: fused_conv_select_k on one 64x1800 frame, K = 16, window 7x25, every
-    pixel a query, all four outputs of the reference op (194.5 MB: HBM-write bound)."""
+    pixel a query, all four outputs of the reference op (194.5 MB: HBM-write bound).  Called through the
+    C ABI with pre-allocated outputs (what the reference's op wrapper hands its Launcher), CUDA events
+    on the launching stream; the 194 MB of outputs exceed L2 every launch."""
     import torch
     H, W, K, kH, kW = 64, 1800, 16, 7, 25
+    N, kt = H * W, kH * kW
     xyz = elo.synth.synth_scan(H, W, seed=0)[None].to(dev)
     idx = elo.synth.hw_index(1, H, W, dev)
-    rhw = torch.randperm(kH * kW, generator=torch.Generator().manual_seed(0)).to(torch.int32).to(dev)
-    kt = kH * kW
-    byts = 4 * (2 * 3 * H * W + 2 * H * W + kt + 3 * H * W * K + H * W * K + 2 * H * W * kt)
+    rhw = torch.randperm(kt, generator=torch.Generator().manual_seed(0)).to(torch.int32).to(dev)
+    o_idx = torch.empty((1, N, K, 3), dtype=torch.int32, device=dev)
+    o_mask = torch.empty((1, N, K, 1), dtype=torch.float32, device=dev)
+    o_valid = torch.empty((1, N, kt, 1), dtype=torch.float32, device=dev)
+    o_vdis = torch.empty((1, N, kt, 1), dtype=torch.float32, device=dev)
+    byts = 4 * (2 * 3 * N + 2 * N + kt + 3 * N * K + N * K + 2 * N * kt)
+    lib = elo._lib.lib()
+
+    def call():
+        rc = lib.elo_fused_conv_select_k(1, H, W, N, kH, kW, K, 0, 1000.0, 1, 1, xyz.data_ptr(), xyz.data_ptr(),
+                                         idx.data_ptr(), rhw.data_ptr(), o_idx.data_ptr(), o_valid.data_ptr(),
+                                         o_vdis.data_ptr(), o_mask.data_ptr(), H, W,
+                                         torch.cuda.current_stream().cuda_stream)
+        elo._lib.check(rc, "elo_fused_conv_select_k")
+
     for _ in range(3):
-        elo.fused_conv_select_k(xyz, xyz, idx, rhw, H, W, H * W, kH, kW, K, 0, 1000.0, 1, 1)
+        call()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize(dev)
     e0.record()
     for _ in range(iters):
-        elo.fused_conv_select_k(xyz, xyz, idx, rhw, H, W, H * W, kH, kW, K, 0, 1000.0, 1, 1)
+        call()
     e1.record()
     torch.cuda.synchronize(dev)
     dur = e0.elapsed_time(e1) * 1e-3 / iters
-    return {"kernel": "fused_conv_index_kernel<select> (64x1800, K=16, 7x25)", "bound": "hbm",
+    return {"kernel": "fused_conv_tiled_kernel<select, 17, 160> (64x1800, K=16, 7x25)", "bound": "hbm",
             "achieved": byts / dur / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
             "frac": byts / dur / 1e9 / peaks["hbm_gbs"], "traffic": None, "avg_launch_us": dur * 1e6,
             "algorithmic_bytes": byts, "peak_source": peaks["src"],
-            "note": "outputs (194 MB) exceed L2 every launch; includes torch's allocation of the four outputs"}
+            "note": "all four outputs of the reference op, pre-allocated; outputs (194 MB) exceed L2 every launch"}
 
 
 def run_ours(args, rank, world, local_rank):
@@ -231,20 +247,55 @@ def run_ours(args, rank, world, local_rank):
             torch.cuda.synchronize(dev)
 
     # ---- value: inputs resident in HBM, K graph replays -------------------------------------------
-    for i in range(args.warmup):
-        engines[i % pool].run()
+    # One forward of a single frame pair is a chain of ~40 dependent single-wave kernels that leaves most of
+    # the 148 SMs idle; --streams S keeps S independent forwards (S different frame pairs, each its own
+    # captured graph, input buffer and scratch) in flight on S streams.  Every step is still one complete
+    # forward of one batch; the timed region is bracketed by events on `stream`, which all S streams fork
+    # from and join back into.
+    S = max(1, args.streams)
+    lanes = [stream] + [torch.cuda.Stream(dev) for _ in range(S - 1)]
+
+    def run_steps(first, count):
+        if S == 1:
+            for i in range(count):
+                engines[(first + i) % pool].run()
+            return
+        fork = torch.cuda.Event()
+        fork.record(stream)
+        for ln in lanes[1:]:
+            ln.wait_event(fork)
+        for i in range(count):
+            eng = engines[(first + i) % pool]
+            eng.stream = lanes[i % S]
+            eng.run()
+        for ln in lanes[1:]:
+            join = torch.cuda.Event()
+            join.record(ln)
+            stream.wait_event(join)
+
+    def timed(first, count):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(stream):
+            e0.record(stream)
+            run_steps(first, count)
+            e1.record(stream)
+        barrier()
+        return e0.elapsed_time(e1)
+
+    with torch.cuda.stream(stream):
+        run_steps(0, args.warmup)
     barrier()
     sampler = ClockSampler(local_rank)
     sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with torch.cuda.stream(stream):
-        e0.record(stream)
-        for i in range(args.steps):
-            engines[(args.warmup + i) % pool].run()
-        e1.record(stream)
-    barrier()
-    ms = e0.elapsed_time(e1)
+    ms = timed(args.warmup, args.steps)
     clocks = sampler.summary()
+    serial_ms = None
+    if S > 1:                      # the same steps one after the other on one stream: the latency of a forward
+        S_keep, S = S, 1
+        for e in engines:
+            e.stream = stream
+        serial_ms = timed(args.warmup, args.steps) / args.steps
+        S = S_keep
     if dist is not None:
         t = torch.tensor([ms], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -259,7 +310,7 @@ def run_ours(args, rank, world, local_rank):
     pinned = [(pc.pin_memory(), T.pin_memory()) for pc, T in host]
     h2d = batch_bytes + B * 64
     d2h = B * 7 * 4
-    pipe = elo.PWCLOPipeline(B, H_IN, W_IN, NPTS, params=store, perms=perms, device=dev)
+    pipe = elo.PWCLOPipeline(B, H_IN, W_IN, NPTS, params=store, perms=perms, device=dev, streams=S)
     feed = lambda n: (pinned[i % len(pinned)] for i in range(n))
     for _ in pipe.run(feed(max(3, args.warmup))):
         pass
@@ -349,11 +400,14 @@ def run_ours(args, rank, world, local_rank):
                                  % (pool, pool * batch_bytes / 1e6),
                            "graph": "kernel-by-kernel launches (--no-graph)" if args.no_graph else
                                     "whole forward captured as one CUDA graph",
+                           "streams": "%d independent forwards in flight on %d CUDA streams (each step = one complete "
+                                      "forward of one batch; --streams 1 runs them back to back)" % (S, S),
+                           "serial_ms_per_forward": serial_ms,
                            "pdl": bool(elo._lib.lib().elo_get_pdl())},
                 "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": "frame-pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": e2e_ms / args.steps, "api": "PWCLOPipeline.run (pinned host batches in, (q,t) out; "
-                        "copies overlap neighbouring batches)", "synchronous_infer": {"value": sync_value,
+                        "copies overlap neighbouring batches; %d forwards in flight)" % S, "synchronous_infer": {"value": sync_value,
                                                                                        "ms_per_step": sync_ms / args.steps}},
                 "gpu_launches": per_forward * args.steps, "launches_per_step": per_forward,
                 "kernel_shares": shares, "roofline": roof, "roofline_index_op": roof_index, "cpu_baseline": cpu,
@@ -376,6 +430,7 @@ def main():
     ap.add_argument("--kernel-times", action="store_true", help="print every kernel's average time to stderr")
     ap.add_argument("--no-graph", action="store_true", help="launch kernel by kernel (for ncu launch lists)")
     ap.add_argument("--pool", type=int, default=0, help="input batches to rotate (0 = enough to exceed L2)")
+    ap.add_argument("--streams", type=int, default=4, help="independent forwards kept in flight (1 = back to back)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     rank = int(os.environ.get("RANK", "0"))

@@ -30,8 +30,13 @@ class PWCLOEngine:
         self.launches_per_forward = None
 
     def _forward(self):
-        return pwclo_model.get_model(self.pc, self.H, self.W, self.T_gt, None, None, False, params=self.store,
-                                     perms=self.perms)
+        # own scratch name space: forwards of different engines may overlap on different streams
+        prev, self.store.scratch_ns = self.store.scratch_ns, id(self)
+        try:
+            return pwclo_model.get_model(self.pc, self.H, self.W, self.T_gt, None, None, False, params=self.store,
+                                         perms=self.perms)
+        finally:
+            self.store.scratch_ns = prev
 
     def capture(self):
         """Warm up eagerly (allocates scratch, sets kernel attributes), then capture one forward."""
@@ -78,27 +83,31 @@ class PWCLOEngine:
 
 
 class PWCLOPipeline:
-    """Streaming inference from host memory: while one captured forward runs, the next batch is uploaded
-    on a copy stream (two engine instances = two input buffers + two graphs, alternating).  Every batch
-    still pays its own host->device copy and device->host read of (q, t); they just overlap the compute
-    of the neighbouring batches, as a deployment that consumes a LiDAR stream would run it."""
+    """Streaming inference from host memory: while captured forwards run, the next batches are uploaded
+    on a copy stream (`depth` engine instances = `depth` input buffers + graphs, used round-robin).  Every
+    batch still pays its own host->device copy and device->host read of (q, t); they just overlap the compute
+    of the neighbouring batches, as a deployment that consumes a LiDAR stream would run it.
+    `streams` > 1 keeps that many forwards in flight at once on separate compute streams: one forward of a
+    single frame pair is a chain of ~40 dependent single-wave kernels that leaves most of the 148 SMs idle,
+    so independent frame pairs overlap almost freely (results are still delivered in order)."""
 
     def __init__(self, batch_size, H_input=64, W_input=1800, num_points=150000, params=None, perms=None,
-                 device="cuda:0", depth=2):
+                 device="cuda:0", depth=None, streams=1):
+        depth = depth if depth is not None else 2 * max(1, streams)
         self.device = torch.device(device)
         store = params if isinstance(params, ParamStore) else ParamStore(
             params if params is not None else init_params(0), self.device)
         self.engines = [PWCLOEngine(batch_size, H_input, W_input, num_points, params=store, perms=perms,
                                     device=device).capture() for _ in range(depth)]
         self.copy_stream = torch.cuda.Stream(self.device)
-        self.compute_stream = torch.cuda.Stream(self.device)
+        self.compute_streams = [torch.cuda.Stream(self.device) for _ in range(max(1, streams))]
         self.uploaded = [torch.cuda.Event() for _ in range(depth)]
         self.consumed = [torch.cuda.Event() for _ in range(depth)]
         self.results = [(torch.empty(batch_size, 4).pin_memory(), torch.empty(batch_size, 3).pin_memory())
                         for _ in range(depth)]
         self.done = [torch.cuda.Event() for _ in range(depth)]
-        for e in self.consumed:
-            e.record(self.compute_stream)
+        for i, e in enumerate(self.consumed):
+            e.record(self.compute_streams[i % len(self.compute_streams)])
 
     def _upload(self, slot, pc, T_gt):
         eng = self.engines[slot]
@@ -111,14 +120,15 @@ class PWCLOPipeline:
 
     def _compute(self, slot):
         eng = self.engines[slot]
-        with torch.cuda.stream(self.compute_stream):
-            self.compute_stream.wait_event(self.uploaded[slot])
+        cs = self.compute_streams[slot % len(self.compute_streams)]
+        with torch.cuda.stream(cs):
+            cs.wait_event(self.uploaded[slot])
             eng.graph.replay()
-            self.consumed[slot].record(self.compute_stream)
+            self.consumed[slot].record(cs)
             q, t = self.results[slot]
             q.copy_(eng.outputs[0], non_blocking=True)
             t.copy_(eng.outputs[1], non_blocking=True)
-            self.done[slot].record(self.compute_stream)
+            self.done[slot].record(cs)
 
     def run(self, batches):
         """batches: iterable of (point_cloud (B,2N,6) pinned host tensor, T_gt or None).  Yields (q, t) host

@@ -21,6 +21,9 @@ class ParamStore:
         self.P = params
         self.device = torch.device(device)
         self._cache = {}
+        # scratch buffers are per name space: every engine that may run concurrently with another one on a
+        # different stream sets its own (engine.PWCLOEngine does) so that their forwards do not share them
+        self.scratch_ns = 0
 
     def stream(self, scopes):
         """Packed weights of a layer chain in the format of the MLP engine currently selected."""
@@ -52,7 +55,7 @@ class ParamStore:
 
     def scratch(self, name, shape, dtype, fill=None):
         """Persistent scratch buffers (projection cell minima, pose-head partials, counters)."""
-        key = ("scratch", name, tuple(shape), dtype)
+        key = ("scratch", self.scratch_ns, name, tuple(shape), dtype)
         if key not in self._cache:
             t = torch.empty(shape, dtype=dtype, device=self.device)
             if fill is not None:
