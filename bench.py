@@ -203,7 +203,8 @@ def index_op_roofline(elo, dev, peaks, iters=20):
     dur = e0.elapsed_time(e1) * 1e-3 / iters
     return {"kernel": "fused_conv_tiled_kernel<select, 17, 160> (64x1800, K=16, 7x25)", "bound": "hbm",
             "achieved": byts / dur / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-            "frac": byts / dur / 1e9 / peaks["hbm_gbs"], "traffic": None, "avg_launch_us": dur * 1e6,
+            "frac": byts / dur / 1e9 / peaks["hbm_gbs"],
+            "traffic": profiled_traffic("elo_fused_conv_select_k[config1]"), "avg_launch_us": dur * 1e6,
             "algorithmic_bytes": byts, "peak_source": peaks["src"],
             "note": "all four outputs of the reference op, pre-allocated; outputs (194 MB) exceed L2 every launch"}
 
