@@ -62,8 +62,12 @@ struct TcPipe {
     //   join():  CTA-wide barrier that publishes all of it.
     // Under programmatic dependent launch begin() runs while the previous kernel is still finishing; the compute
     // warps call pdl_wait() after it, the other two warps never touch upstream data and do not wait at all.
+    // alloc_now = false: tensor memory is claimed later, by alloc_late(), right before the first A operand is
+    // written -- with a second CTA resident on the SM (the weight ring is sized for that) one tile's set-up and
+    // gather then overlap the other's MMA chain, and finish() can be called before the pooling for the same reason.
     __device__ __forceinline__ void begin(float* ring_, uint64_t* bars, uint32_t nring_, uint32_t* tmem_holder_,
-                                          const float* bias_gmem, float* bias_smem, int nbias, long long* tlog_ = nullptr)
+                                          const float* bias_gmem, float* bias_smem, int nbias, long long* tlog_ = nullptr,
+                                          bool alloc_now = true)
     {
         tlog = tlog_;
         stamp(0);
@@ -80,7 +84,16 @@ struct TcPipe {
         // every epilogue needs its biases at once: one L2 round trip here instead of one per layer
         if (warp == COMPUTE_WARPS + 1)
             for (int i = lane; i < nbias; i += 32) bias_smem[i] = __ldg(bias_gmem + i);
-        if (warp == 0) tc::tmem_alloc(tmem_holder, tc::TMEM_COLS);
+        if (warp == 0 && alloc_now) tc::tmem_alloc(tmem_holder, tc::TMEM_COLS);
+    }
+    // compute warps only (all of them): blocks until the SM's tensor memory is free
+    __device__ __forceinline__ void alloc_late()
+    {
+        if ((threadIdx.x >> 5) == 0) tc::tmem_alloc(tmem_holder, tc::TMEM_COLS);
+        tc::fence_before_sync();
+        compute_sync();
+        tc::fence_after_sync();
+        tbase = *reinterpret_cast<volatile uint32_t*>(tmem_holder);
     }
     __device__ __forceinline__ void join()
     {
@@ -130,6 +143,7 @@ struct TcPipe {
         constexpr uint32_t KSTEP16 = 2u * N;           // 16-byte units between consecutive K-steps of B
         mbar_wait(a_ready, layer & 1u);
         tc::fence_after_sync();
+        tbase = *reinterpret_cast<volatile uint32_t*>(tmem_holder);    // late allocation: known once A is ready
         stamp(2 + 2 * (int)layer);
         const uint32_t nks = (cin + 7u) >> 3;
         const uint32_t idesc = tc::idesc_tf32(N);

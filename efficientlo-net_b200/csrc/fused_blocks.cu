@@ -596,7 +596,7 @@ __device__ __forceinline__ float pool_softmax(const float* SL, const float* SV, 
     return a / s;
 }
 
-__global__ void __launch_bounds__(TC_LAUNCH_THREADS, 1) group_mlp_max_tc_kernel(const GroupMlpParams p)
+__global__ void __launch_bounds__(TC_LAUNCH_THREADS, 2) group_mlp_max_tc_kernel(const GroupMlpParams p)
 {
     constexpr int RS = TC_ROWS;
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -618,7 +618,7 @@ __global__ void __launch_bounds__(TC_LAUNCH_THREADS, 1) group_mlp_max_tc_kernel(
     int nbias = 0;
     for (int l = 0; l < p.nl; ++l) nbias += p.cout[l];
     pipe.begin(sm.ring, sm.bars, p.nring, sm.tmem_holder, p.weights[set] + (size_t)p.total_chunks * TC_CHUNK_FLOATS,
-               sm.bias, nbias, p.tlog);
+               sm.bias, nbias, p.tlog, /*alloc_now=*/false);
     if (warp < COMPUTE_WARPS) {
         pdl_wait();                              // from here on: data written by earlier kernels
         if (p.nbr_in[set] != nullptr) tc_load_nbr(p.qs, rows, p.xyz1, p.nbr_in[set], q0, p.qt, total_q, nbr, ctr);
@@ -660,7 +660,7 @@ __global__ void __launch_bounds__(TC_LAUNCH_THREADS, 1) group_mlp_max_tc_kernel(
         if (ql < 0 || ql >= p.qt || nbr[r] < 0) return -1;
         return (long long)__float_as_int(ctr[ql * 4 + 3]) * cells2 + nbr[r];
     });
-    compute_sync();
+    pipe.alloc_late();                           // (a barrier of the compute warps: the gather above is complete)
     pipe.load_a_from_smem(X, 0, cin0, 0);
     pipe.signal_a_ready();
     const int m = pipe.my_row();
@@ -674,7 +674,7 @@ __global__ void __launch_bounds__(TC_LAUNCH_THREADS, 1) group_mlp_max_tc_kernel(
         });
         if (!last) pipe.signal_a_ready();
     }
-    compute_sync();
+    pipe.finish();                               // (a barrier too) tensor memory goes to the SM's other tile now
     // max over the K neighbours of (y * mask): y >= 0 after ReLU, masked rows count as 0
     float* out = p.out[set];
     for (int t = threadIdx.x; t < p.qt * cout_last; t += CTA_THREADS) {
@@ -693,7 +693,6 @@ __global__ void __launch_bounds__(TC_LAUNCH_THREADS, 1) group_mlp_max_tc_kernel(
             rows.decode(r, q2, k2);
             if (q2 >= 0 && q2 < p.qt && q0 + q2 < total_q) p.dbg_nbr[set][(q0 + q2) * g.K + k2] = nbr[r];
         }
-    pipe.finish();
 }
 
 __global__ void __launch_bounds__(TC_LAUNCH_THREADS, 1) cost_volume_1_tc_kernel(const Cv1Params p)
@@ -1006,6 +1005,9 @@ static int set_smem(Kernel k, size_t bytes, const char* what)
 {
     cudaError_t err = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
     if (err != cudaSuccess) return set_cuda_error(err, what);
+    // all of the SM's L1/shared array as shared memory: two ~110 KB tiles are meant to be resident together
+    err = cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
+    if (err != cudaSuccess) return set_cuda_error(err, what);
     return 0;
 }
 
@@ -1071,9 +1073,9 @@ static int g_engine = 1;
 struct TcChoice { int per_tile, tiles; };
 
 // 128-row tiles: `units` work items of `rows_per_unit` rows, spread evenly over the waves they need
-static TcChoice choose_tc_tile(long long units, int rows_per_unit, int nsets)
+static TcChoice choose_tc_tile(long long units, int rows_per_unit, int nsets, int ctas_per_sm = 1)
 {
-    const int sms = device_info().sm_count;
+    const int sms = device_info().sm_count * ctas_per_sm;
     // a query's rows never straddle a 32-row lane quarter (TcRows): 4 * floor(32 / K) queries per tile
     const int cap = rows_per_unit > 1 ? 4 * (32 / rows_per_unit) : TC_ROWS;
     long long tiles = (units + cap - 1) / cap;
@@ -1093,8 +1095,17 @@ static size_t tc_base_smem(int kt, size_t staging_floats)
            align16(TC_ROWS * 4) + align16(TC_ROWS * 16) + align16(staging_floats * 4);
 }
 
-static int tc_pick_ring(size_t base, int total_chunks)
+// shared memory one CTA may use when two are to be resident on an SM (228 KB per SM, 1 KB reserved per CTA,
+// 1 KB of static shared memory in these kernels)
+static constexpr int SMEM_HALF = 112 * 1024;
+
+static int tc_pick_ring(size_t base, int total_chunks, bool two_per_sm = false)
 {
+    if (two_per_sm) {
+        long long n2 = ((long long)SMEM_HALF - (long long)base) / TC_CHUNK_BYTES;
+        if (n2 > total_chunks) n2 = total_chunks;
+        if (n2 >= 3 || n2 == total_chunks) return (int)(n2 > MAX_RING ? MAX_RING : n2);
+    }
     long long n = ((long long)SMEM_LIMIT - (long long)base) / TC_CHUNK_BYTES;
     if (n > MAX_RING) n = MAX_RING;
     if (n > total_chunks) n = total_chunks;
@@ -1174,9 +1185,10 @@ extern "C" int elo_group_mlp_max(const elo_group_mlp_desc* d, void* stream)
         p.total_chunks = chunks_t;
         const int pool_ld = p.cout[p.nl - 1] + 1;
         const size_t base = tc_base_smem(kt, (size_t)(xch > pool_ld ? xch : pool_ld) * TC_ROWS);
-        p.nring = tc_pick_ring(base, chunks_t);
+        p.nring = tc_pick_ring(base, chunks_t, /*two_per_sm=*/true);
         if (p.nring < 2) return set_error(ELO_ERR_UNSUPPORTED, "group_mlp_max: tile does not fit shared memory");
-        const TcChoice tc = choose_tc_tile(per_set, p.g.K, d->nsets);
+        const bool two = base + (size_t)p.nring * TC_CHUNK_BYTES <= (size_t)SMEM_HALF;
+        const TcChoice tc = choose_tc_tile(per_set, p.g.K, d->nsets, two ? 2 : 1);
         p.qt = tc.per_tile;
         return launch_tc(group_mlp_max_tc_kernel, p, dim3(tc.tiles, d->nsets), base + (size_t)p.nring * TC_CHUNK_BYTES,
                          (cudaStream_t)stream, "group_mlp_max (tensor core) launch");

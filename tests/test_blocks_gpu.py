@@ -278,6 +278,25 @@ def test_engine_graph_replay_is_deterministic(elo, world):
     close(t1, world["out"][1], "engine t", atol=2e-5)
 
 
+def test_pipeline_with_forwards_in_flight_keeps_order_and_values(elo, world):
+    """PWCLOPipeline(streams=3): three independent forwards overlap on three streams (own graph, input buffer and
+    scratch each); every batch must come back in order with the values a lone engine computes for it."""
+    dev = world["dev"]
+    B = 1
+    batches = [elo.synth.synth_batch(B, H_IN, W_IN, NPTS, seed0=50 + i) for i in range(7)]
+    pinned = [(pc.pin_memory(), T.pin_memory()) for pc, T in batches]
+    eng = elo.PWCLOEngine(B, H_IN, W_IN, NPTS, params=world["store"], perms=world["perms"], device=dev).capture()
+    want = [tuple(x.clone() for x in eng.infer(pc, T)) for pc, T in pinned]
+    pipe = elo.PWCLOPipeline(B, H_IN, W_IN, NPTS, params=world["store"], perms=world["perms"], device=dev, streams=3)
+    for rep in range(2):            # the second pass reuses every slot
+        got = [(q.clone(), t.clone()) for q, t in pipe.run(iter(pinned))]
+        assert len(got) == len(want)
+        for i, ((q, t), (qw, tw)) in enumerate(zip(got, want)):
+            assert torch.allclose(q, qw, rtol=0, atol=1e-6) and torch.allclose(t, tw, rtol=0, atol=1e-6), (rep, i)
+    # different inputs do give different poses (the comparison above is not vacuous)
+    assert not torch.allclose(want[0][1], want[1][1], rtol=0, atol=1e-4)
+
+
 def test_forward_128x2048_matches_oracle(elo, cuda, mlp_engine):
     """BASELINE.json configs[4] geometry: a dense 128x2048 scan (pyramid 32x256 / 16x128 / 8x64 / 8x32)."""
     if mlp_engine == 0:
