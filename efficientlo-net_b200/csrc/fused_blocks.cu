@@ -143,6 +143,7 @@ struct Cv1Params {
     Window g;
     long long total_q;
     int qt, C, total_chunks, nring;
+    int sl_in_ring;      // tensor-core engine: the logits' pool staging aliases the (by then dead) weight ring
     const float* xyz1;
     const float* xyz2;
     const float* f1;
@@ -695,12 +696,12 @@ __global__ void __launch_bounds__(TC_LAUNCH_THREADS, 2) group_mlp_max_tc_kernel(
         }
 }
 
-__global__ void __launch_bounds__(TC_LAUNCH_THREADS, 1) cost_volume_1_tc_kernel(const Cv1Params p)
+__global__ void __launch_bounds__(TC_LAUNCH_THREADS, 2) cost_volume_1_tc_kernel(const Cv1Params p)
 {
     constexpr int RS = TC_ROWS;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int C = p.C, xc = 10 + 2 * C;
-    TcSmem sm = tc_carve(smem_raw, p.nring, 0, (size_t)max(((xc + 3) & ~3), 2 * POOL_LD64) * RS);
+    TcSmem sm = tc_carve(smem_raw, p.nring, 0, (size_t)max(((xc + 3) & ~3), (p.sl_in_ring ? 1 : 2) * POOL_LD64) * RS);
     const int warp = threadIdx.x >> 5;
     const Window g = p.g;
     const TcRows rows(g.K);
@@ -710,7 +711,7 @@ __global__ void __launch_bounds__(TC_LAUNCH_THREADS, 1) cost_volume_1_tc_kernel(
     pdl_trigger();
     TcPipe pipe;
     pipe.begin(sm.ring, sm.bars, p.nring, sm.tmem_holder, p.weights + (size_t)p.total_chunks * TC_CHUNK_FLOATS,
-               sm.bias, 128 + 64 + 64 + 64 + 128 + 64, p.tlog);
+               sm.bias, 128 + 64 + 64 + 64 + 128 + 64, p.tlog, /*alloc_now=*/false);
     if (warp < COMPUTE_WARPS) {
         pdl_wait();
         tc_load_nbr(p.qs, rows, p.xyz1, p.nbr_in, q0, p.qt, p.total_q, nbr, ctr);
@@ -750,7 +751,7 @@ __global__ void __launch_bounds__(TC_LAUNCH_THREADS, 1) cost_volume_1_tc_kernel(
             return (long long)((q0 + ql) / nq) * cells + nbr[r];
         });
     }
-    compute_sync();
+    pipe.alloc_late();                          // (a barrier of the compute warps: the gather above is complete)
     pipe.stamp(3);
     const int m = pipe.my_row();
     // the 10 xyz channels are needed again by CV_xyz after the tile's A region has been overwritten
@@ -761,8 +762,10 @@ __global__ void __launch_bounds__(TC_LAUNCH_THREADS, 1) cost_volume_1_tc_kernel(
     pipe.signal_a_ready();
     pipe.stamp(4);
     // pool staging (the X region is dead once every thread has loaded its row): F and logits as [row][65]
+    // The logits are written by the LAST epilogue, when every MMA has completed and the weight ring is dead:
+    // with sl_in_ring they go there, which keeps the tile small enough for two to be resident per SM.
     float* SF = X;
-    float* SL = X + RS * POOL_LD64;
+    float* SL = p.sl_in_ring ? sm.ring : X + RS * POOL_LD64;
     pipe.epilogue<true>(128, [&](int b, const float (&v)[16]) { pipe.store_a(0, b, v); });        // CV_0
     pipe.signal_a_ready();
     pipe.epilogue<true>(64, [&](int b, const float (&v)[16]) { pipe.store_a(0, b, v); });         // CV_1
@@ -788,7 +791,7 @@ __global__ void __launch_bounds__(TC_LAUNCH_THREADS, 1) cost_volume_1_tc_kernel(
 #pragma unroll
         for (int i = 0; i < 16; ++i) SL[m * POOL_LD64 + b * 16 + i] = v[i];
     });
-    compute_sync();
+    pipe.finish();                              // (a barrier too) tensor memory goes to the SM's other tile now
     pipe.stamp(5);
     for (int t = threadIdx.x; t < p.qt * 64; t += CTA_THREADS) {
         const int ql = t >> 6, c = t & 63;
@@ -803,7 +806,6 @@ __global__ void __launch_bounds__(TC_LAUNCH_THREADS, 1) cost_volume_1_tc_kernel(
             rows.decode(r, q2, k2);
             if (q2 >= 0 && q2 < p.qt && q0 + q2 < p.total_q) p.dbg_nbr[(q0 + q2) * g.K + k2] = nbr[r];
         }
-    pipe.finish();
     pipe.stamp(7);
 }
 
@@ -1075,10 +1077,13 @@ struct TcChoice { int per_tile, tiles; };
 // 128-row tiles: `units` work items of `rows_per_unit` rows, spread evenly over the waves they need
 static TcChoice choose_tc_tile(long long units, int rows_per_unit, int nsets, int ctas_per_sm = 1)
 {
-    const int sms = device_info().sm_count * ctas_per_sm;
     // a query's rows never straddle a 32-row lane quarter (TcRows): 4 * floor(32 / K) queries per tile
     const int cap = rows_per_unit > 1 ? 4 * (32 / rows_per_unit) : TC_ROWS;
     long long tiles = (units + cap - 1) / cap;
+    // Two tiles resident on an SM take turns on its tensor memory: that pays when the work needs more than one
+    // wave of full tiles anyway; a call that fits one tile per SM keeps the SMs to itself.
+    int sms = device_info().sm_count;
+    if (tiles * nsets > sms) sms *= ctas_per_sm;
     const long long waves = (tiles * nsets + sms - 1) / sms;
     long long slots = waves * sms / nsets;
     if (slots < tiles) slots = tiles;
@@ -1224,6 +1229,7 @@ extern "C" int elo_cost_volume_1(const elo_cost_volume_desc* d, void* stream)
     if (d->window_q.K > 64) return set_error(ELO_ERR_UNSUPPORTED, "cost_volume_1: nsample_q > 64");
     if (d->batch_size == 0) return ELO_OK;
     Cv1Params p;
+    p.sl_in_ring = 0;
     p.qs.H1 = d->H; p.qs.W1 = d->W; p.qs.oh = d->H; p.qs.ow = d->W; p.qs.qs_h = 1; p.qs.qs_w = 1;
     p.g = make_window(&d->window_q);
     p.total_q = (long long)d->batch_size * d->H * d->W;
@@ -1239,10 +1245,16 @@ extern "C" int elo_cost_volume_1(const elo_cost_volume_desc* d, void* stream)
         p.total_chunks = tc_layer_chunks(xc, 128) + tc_layer_chunks(128, 64) + tc_layer_chunks(64, 64) +
                          tc_layer_chunks(10, 64) + tc_layer_chunks(128, 128) + tc_layer_chunks(128, 64);
         if (p.g.K > 32) return set_error(ELO_ERR_UNSUPPORTED, "cost_volume_1: the tensor-core engine takes nsample_q <= 32");
-        const size_t base = tc_base_smem(0, (size_t)(xch > 130 ? xch : 130) * TC_ROWS);
-        p.nring = tc_pick_ring(base, p.total_chunks);
+        // two tiles per SM when the logits' pool staging can live in the weight ring (>= 3 slots hold 128 x 65 floats)
+        size_t base = tc_base_smem(0, (size_t)(xch > POOL_LD64 ? xch : POOL_LD64) * TC_ROWS);
+        p.nring = tc_pick_ring(base, p.total_chunks, /*two_per_sm=*/true);
+        p.sl_in_ring = (p.nring >= 3 && base + (size_t)p.nring * TC_CHUNK_BYTES <= (size_t)SMEM_HALF) ? 1 : 0;
+        if (!p.sl_in_ring) {
+            base = tc_base_smem(0, (size_t)(xch > 2 * POOL_LD64 ? xch : 2 * POOL_LD64) * TC_ROWS);
+            p.nring = tc_pick_ring(base, p.total_chunks);
+        }
         if (p.nring < 2) return set_error(ELO_ERR_UNSUPPORTED, "cost_volume_1: tile does not fit shared memory");
-        const TcChoice tc = choose_tc_tile(p.total_q, p.g.K, 1);
+        const TcChoice tc = choose_tc_tile(p.total_q, p.g.K, 1, p.sl_in_ring ? 2 : 1);
         p.qt = tc.per_tile;
         p.g.kt = 0;
         return launch_tc(cost_volume_1_tc_kernel, p, dim3(tc.tiles), base + (size_t)p.nring * TC_CHUNK_BYTES,
