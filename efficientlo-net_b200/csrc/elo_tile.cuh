@@ -111,17 +111,32 @@ template <typename CellOf>
 __device__ __forceinline__ void gather_features(float* X, int RS, int c0, const float* __restrict__ src, int C,
                                                 int rows, CellOf cell_of)
 {
-    const int c4n = C >> 2;
-    for (int t = threadIdx.x; t < rows * c4n; t += CTA_THREADS) {
-        const int r = t / c4n, c4 = t - r * c4n;
-        const long long cell = cell_of(r);
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (cell >= 0) v = __ldg(reinterpret_cast<const float4*>(src + (size_t)cell * C) + c4);
-        const int c = c0 + c4 * 4;
-        X[act_index(c + 0, r, RS)] = v.x;
-        X[act_index(c + 1, r, RS)] = v.y;
-        X[act_index(c + 2, r, RS)] = v.z;
-        X[act_index(c + 3, r, RS)] = v.w;
+    // four tasks per thread and trip: their (L2-latency) loads are in flight together
+    constexpr int U = 4;
+    const int c4n = C >> 2, total = rows * c4n;
+    for (int t0 = threadIdx.x; t0 < total; t0 += CTA_THREADS * U) {
+        float4 v[U];
+        int rr[U], cc[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int t = t0 + u * CTA_THREADS;
+            v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            rr[u] = -1; cc[u] = 0;
+            if (t < total) {
+                const int r = t / c4n, c4 = t - r * c4n;
+                const long long cell = cell_of(r);
+                if (cell >= 0) v[u] = __ldg(reinterpret_cast<const float4*>(src + (size_t)cell * C) + c4);
+                rr[u] = r; cc[u] = c0 + c4 * 4;
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (rr[u] < 0) continue;
+            X[act_index(cc[u] + 0, rr[u], RS)] = v[u].x;
+            X[act_index(cc[u] + 1, rr[u], RS)] = v[u].y;
+            X[act_index(cc[u] + 2, rr[u], RS)] = v[u].z;
+            X[act_index(cc[u] + 3, rr[u], RS)] = v[u].w;
+        }
     }
 }
 

@@ -580,19 +580,34 @@ constexpr int POOL_LD64 = 65;
 __device__ __forceinline__ float pool_softmax(const float* SL, const float* SV, int ld_v, const int* nbr, int r0, int K,
                                               int c)
 {
-    // online form: one pass over the K rows.  __expf (ex2.approx) is accurate to ~1e-6 relative on the
-    // arguments (<= 0) seen here, two orders below the parity bar.
+    // Online form over chunks of 8 rows: a chunk's loads, its exponentials and its sums are independent of each
+    // other (K = 4 / 6 / 32 in the model: one chunk is the common case), only the running maximum couples the
+    // chunks.  __expf (ex2.approx) is accurate to ~1e-6 relative on the arguments (<= 0) seen here, two orders
+    // below the parity bar.
     float m = -INFINITY, s = 0.f, a = 0.f;
-    for (int k = 0; k < K; ++k) {
-        const float l = nbr[r0 + k] >= 0 ? SL[(r0 + k) * POOL_LD64 + c] : -1e10f;
-        const float v = SV[(r0 + k) * ld_v + c];
-        if (l > m) {
-            const float sc = __expf(m - l);
-            s *= sc; a *= sc; m = l;
+    for (int k0 = 0; k0 < K; k0 += 8) {
+        float l[8], v[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int k = k0 + i;
+            l[i] = -INFINITY; v[i] = 0.f;
+            if (k < K) {
+                l[i] = nbr[r0 + k] >= 0 ? SL[(r0 + k) * POOL_LD64 + c] : -1e10f;
+                v[i] = SV[(r0 + k) * ld_v + c];
+            }
         }
-        const float e = __expf(l - m);
-        s += e;
-        a = fmaf(e, v, a);
+        float mn = m;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) mn = fmaxf(mn, l[i]);
+        const float sc = __expf(m - mn);          // first chunk: exp(-inf) = 0 on s = a = 0
+        s *= sc; a *= sc;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const float e = __expf(l[i] - mn);      // rows past K: exp(-inf) = 0
+            s += e;
+            a = fmaf(e, v[i], a);
+        }
+        m = mn;
     }
     return a / s;
 }
