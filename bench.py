@@ -431,7 +431,7 @@ def main():
     ap.add_argument("--kernel-times", action="store_true", help="print every kernel's average time to stderr")
     ap.add_argument("--no-graph", action="store_true", help="launch kernel by kernel (for ncu launch lists)")
     ap.add_argument("--pool", type=int, default=0, help="input batches to rotate (0 = enough to exceed L2)")
-    ap.add_argument("--streams", type=int, default=4, help="independent forwards kept in flight (1 = back to back)")
+    ap.add_argument("--streams", type=int, default=6, help="independent forwards kept in flight (1 = back to back)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     rank = int(os.environ.get("RANK", "0"))

@@ -13,6 +13,7 @@
 // of shared memory; (5) the reduction over the K neighbours (max, or masked softmax-weighted sum)
 // writes (B,N,C_out) once.  Inference batch-norm is folded into the weights on the host.
 #include <cuda_runtime.h>
+#include <stdlib.h>
 #include <math.h>
 
 #include "../../include/elo_b200.h"
@@ -1119,6 +1120,8 @@ static size_t tc_base_smem(int kt, size_t staging_floats)
 // 1 KB of static shared memory in these kernels)
 static constexpr int SMEM_HALF = 112 * 1024;
 
+static int g_ring_alone = getenv("ELO_TC_RING") ? atoi(getenv("ELO_TC_RING")) : 3;     // measured: 3..8 slots give the same tile latency
+
 static int tc_pick_ring(size_t base, int total_chunks, bool two_per_sm = false)
 {
     if (two_per_sm) {
@@ -1127,6 +1130,9 @@ static int tc_pick_ring(size_t base, int total_chunks, bool two_per_sm = false)
         if (n2 >= 3 || n2 == total_chunks) return (int)(n2 > MAX_RING ? MAX_RING : n2);
     }
     long long n = ((long long)SMEM_LIMIT - (long long)base) / TC_CHUNK_BYTES;
+    // a tile that has the SM to itself still leaves room for the small kernels of other forwards in flight
+    // (searches, projections, pose heads): TC_RING_ALONE slots keep the MMA warp fed (g_ring_alone, tunable)
+    if (n > g_ring_alone) n = g_ring_alone;
     if (n > MAX_RING) n = MAX_RING;
     if (n > total_chunks) n = total_chunks;
     return (int)n;
