@@ -842,7 +842,7 @@ __global__ void __launch_bounds__(TC_LAUNCH_THREADS, 1) cost_volume_2_tc_kernel(
     pdl_trigger();
     TcPipe pipe;
     pipe.begin(sm.ring, sm.bars, p.nring, sm.tmem_holder, p.weights + (size_t)p.total_chunks * TC_CHUNK_FLOATS,
-               sm.bias, 64 + 128 + 64, p.tlog);
+               sm.bias, 64 + 128 + 64, p.tlog, /*alloc_now=*/false);
     if (warp < COMPUTE_WARPS) {
         pdl_wait();
         tc_load_nbr(p.qs, rows, p.xyz1, p.nbr_in, q0, p.qt, p.total_q, nbr, ctr);
@@ -877,7 +877,7 @@ __global__ void __launch_bounds__(TC_LAUNCH_THREADS, 1) cost_volume_2_tc_kernel(
             return (long long)((q0 + ql) / nq) * cells + nbr[r];
         });
     }
-    compute_sync();
+    pipe.alloc_late();                          // (a barrier of the compute warps: the gather above is complete)
     pipe.load_a_from_smem(X, 0, 10, 0);
     pipe.load_a_from_smem(X, 16, C + 64, 64);
     pipe.signal_a_ready();
@@ -894,7 +894,7 @@ __global__ void __launch_bounds__(TC_LAUNCH_THREADS, 1) cost_volume_2_tc_kernel(
 #pragma unroll
         for (int i = 0; i < 16; ++i) SL[m * POOL_LD64 + b * 16 + i] = v[i];
     });
-    compute_sync();
+    pipe.finish();                              // (a barrier too) tensor memory is free while this tile pools
     for (int t = threadIdx.x; t < p.qt * 64; t += CTA_THREADS) {
         const int ql = t >> 6, c = t & 63;
         const long long gq = q0 + ql;
@@ -907,7 +907,6 @@ __global__ void __launch_bounds__(TC_LAUNCH_THREADS, 1) cost_volume_2_tc_kernel(
             rows.decode(r, q2, k2);
             if (q2 >= 0 && q2 < p.qt && q0 + q2 < p.total_q) p.dbg_nbr[(q0 + q2) * g.K + k2] = nbr[r];
         }
-    pipe.finish();
 }
 
 __global__ void __launch_bounds__(TC_LAUNCH_THREADS, 1) row_mlp_tc_kernel(const RowMlpParams p)
@@ -921,8 +920,11 @@ __global__ void __launch_bounds__(TC_LAUNCH_THREADS, 1) row_mlp_tc_kernel(const 
     int nbias = 0;
     for (int ph = 0; ph < p.nphase; ++ph)
         for (int l = 0; l < p.nl[ph]; ++l) nbias += p.cout[ph][l];
-    pipe.init(sm.ring, sm.bars, p.nring, sm.tmem_holder, p.weights[set] + (size_t)p.total_chunks * TC_CHUNK_FLOATS,
-              sm.bias, nbias, p.tlog);
+    // Tensor memory is claimed only after the dependent-launch wait and the gather (alloc_late): no tile of this
+    // library ever holds it while waiting for another kernel, whatever shares the SM with it.
+    pipe.begin(sm.ring, sm.bars, p.nring, sm.tmem_holder, p.weights[set] + (size_t)p.total_chunks * TC_CHUNK_FLOATS,
+               sm.bias, nbias, p.tlog, /*alloc_now=*/false);
+    pipe.join();
     if (warp == COMPUTE_WARPS) { pipe.produce(p.weights[set], p.total_chunks); return; }
     if (warp == COMPUTE_WARPS + 1) {
         if (tc::elect_one())
@@ -947,7 +949,7 @@ __global__ void __launch_bounds__(TC_LAUNCH_THREADS, 1) row_mlp_tc_kernel(const 
                 });
             }
         }
-    compute_sync();
+    pipe.alloc_late();                          // (a barrier of the compute warps: the gather above is complete)
     const int m = pipe.my_row();
     const bool row_ok = m < rt && r0 + m < rows;
     for (int ph = 0; ph < p.nphase; ++ph) {
