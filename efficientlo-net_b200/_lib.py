@@ -7,6 +7,9 @@ import os
 
 from .build import LIB
 
+# ELO_B200_LIB: another build of the same library (A/B timing of two builds on one box)
+LIB = os.environ.get("ELO_B200_LIB") or LIB
+
 _c_int, _c_float, _c_void_p = ctypes.c_int, ctypes.c_float, ctypes.c_void_p
 
 _c_ll, _c_uint = ctypes.c_longlong, ctypes.c_uint
