@@ -139,6 +139,44 @@ def test_select_k_near_ties_take_the_exact_path(elo, cuda):
     cases.assert_same(cases.call(cuda_impl(elo, cuda), case), cases.call(io.port, case, nthreads=8), "near ties")
 
 
+@pytest.mark.parametrize("mode", ["select", "random"])
+def test_unaligned_output_buffers(elo, cuda, mode):
+    """Output pointers that are only 4-byte aligned (views into larger buffers): the kernels fall back from
+    16-byte to scalar stores and must write exactly the same rows, and nothing outside them."""
+    rng = np.random.default_rng(21)
+    case = raster_case(rng, mode, 2, 6, 50, 5, 9, 8, 1, 1, 3.0, flag_copy=1)
+    want = cases.call(io.port, case, nthreads=8)
+    B, N, K, kt = 2, case["npoints"], case["K"], 45
+    t = {k: torch.as_tensor(case[k]).to(cuda) for k in ("xyz1", "xyz2", "idx_n2", "random_hw")}
+    pad = 3                                           # elements in front: 12 bytes off a 16-byte boundary
+    bufs = {"idx": torch.full((pad + B * N * K * 3 + 5,), -7, dtype=torch.int32, device=cuda),
+            "valid": torch.full((pad + B * N * kt + 5,), -7.0, device=cuda),
+            "vdis": torch.full((pad + B * N * kt + 5,), -7.0, device=cuda),
+            "mask": torch.full((pad + B * N * K + 5,), -7.0, device=cuda)}
+    lib = elo._lib.lib()
+    fn = lib.elo_fused_conv_select_k if mode == "select" else lib.elo_fused_conv_random_k
+    ptr = lambda name: bufs[name].data_ptr() + 4 * pad
+    rc = fn(B, 6, 50, N, 5, 9, K, 1, 3.0, 1, 1, t["xyz1"].data_ptr(), t["xyz2"].data_ptr(), t["idx_n2"].data_ptr(),
+            t["random_hw"].data_ptr(), ptr("idx"), ptr("valid"), ptr("vdis"), ptr("mask"), 6, 50,
+            torch.cuda.current_stream().cuda_stream)
+    assert rc == 0
+    torch.cuda.synchronize()
+    got = (bufs["idx"][pad:-5].reshape(B, N, K, 3), bufs["valid"][pad:-5].reshape(B, N, kt, 1),
+           bufs["vdis"][pad:-5].reshape(B, N, kt, 1), bufs["mask"][pad:-5].reshape(B, N, K, 1))
+    cases.assert_same(tuple(g.cpu().numpy() for g in got), want, "unaligned " + mode)
+    for b in bufs.values():                            # guard elements untouched
+        assert (b[:pad] == -7).all() and (b[-5:] == -7).all()
+
+
+@pytest.mark.parametrize("kH,kW", [(31, 33), (33, 33)])
+def test_select_k_large_windows(elo, cuda, kH, kW):
+    """Windows around the 1024-cell limit of the tiled kernel's parameter-resident walk table (1023 cells: tiled;
+    1089: the warp-per-query kernel takes the call even when the tiled one is requested)."""
+    rng = np.random.default_rng(31)
+    case = raster_case(rng, "select", 1, 40, 48, kH, kW, 16, 1, 1, 1000.0, holes=0.3)
+    cases.assert_same(cases.call(cuda_impl(elo, cuda), case), cases.call(io.port, case, nthreads=8), "window %dx%d" % (kH, kW))
+
+
 def test_golden_vectors(elo, cuda):
     g = np.load(GOLDEN)
     for i in range(int(g["n_cases"])):
