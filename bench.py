@@ -220,6 +220,8 @@ def run_ours(args, rank, world, local_rank):
         dist.init_process_group("nccl", device_id=dev)
     B = args.batch
     elo._lib.set_mlp_engine(1 if args.engine == "tc" else 0)
+    policy = args.tile_policy if args.tile_policy >= 0 else (1 if args.streams > 1 else 0)
+    elo._lib.set_tile_policy(policy)
     store = elo.ParamStore(elo.params.init_params(0), dev)
     perms = elo.params.make_perms(0)
     # distinct input batches, rotated so that every step reads inputs that are cold in L2
@@ -404,6 +406,7 @@ def run_ours(args, rank, world, local_rank):
                            "streams": "%d independent forwards in flight on %d CUDA streams (each step = one complete "
                                       "forward of one batch; --streams 1 runs them back to back)" % (S, S),
                            "serial_ms_per_forward": serial_ms,
+                           "tile_policy": "throughput (full 128-row tiles)" if policy == 1 else "latency (small calls spread over all SMs)",
                            "pdl": bool(elo._lib.lib().elo_get_pdl())},
                 "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": "frame-pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
@@ -431,7 +434,8 @@ def main():
     ap.add_argument("--kernel-times", action="store_true", help="print every kernel's average time to stderr")
     ap.add_argument("--no-graph", action="store_true", help="launch kernel by kernel (for ncu launch lists)")
     ap.add_argument("--pool", type=int, default=0, help="input batches to rotate (0 = enough to exceed L2)")
-    ap.add_argument("--streams", type=int, default=6, help="independent forwards kept in flight (1 = back to back)")
+    ap.add_argument("--tile-policy", type=int, default=-1, help="tensor-core tiles: 0 latency, 1 throughput, -1 by --streams")
+    ap.add_argument("--streams", type=int, default=12, help="independent forwards kept in flight (1 = back to back)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     rank = int(os.environ.get("RANK", "0"))

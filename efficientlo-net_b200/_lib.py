@@ -123,6 +123,10 @@ def lib():
         handle.elo_set_index_kernel.restype = _c_int
         handle.elo_get_index_kernel.argtypes = []
         handle.elo_get_index_kernel.restype = _c_int
+        handle.elo_set_tile_policy.argtypes = [_c_int]
+        handle.elo_set_tile_policy.restype = _c_int
+        handle.elo_get_tile_policy.argtypes = []
+        handle.elo_get_tile_policy.restype = _c_int
         handle.elo_set_pdl.argtypes = [_c_int]
         handle.elo_set_pdl.restype = _c_int
         handle.elo_get_pdl.argtypes = []
@@ -172,6 +176,11 @@ def set_mlp_engine(engine):
 def set_index_kernel(which):
     """0: choose by query count, 1: tile-staged thread-per-query kernel, 2: one warp per query."""
     check(lib().elo_set_index_kernel(int(which)), "elo_set_index_kernel")
+
+
+def set_tile_policy(policy):
+    """0: latency (spread small calls over all SMs), 1: throughput (full 128-row tiles)."""
+    check(lib().elo_set_tile_policy(int(policy)), "elo_set_tile_policy")
 
 
 def set_pdl(on):

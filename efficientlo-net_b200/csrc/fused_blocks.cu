@@ -1092,6 +1092,8 @@ static int g_engine = 1;
 
 struct TcChoice { int per_tile, tiles; };
 
+static int g_tile_policy = (getenv("ELO_TILE_POLICY") && getenv("ELO_TILE_POLICY")[0] == '1') ? 1 : 0;   // 0: latency (spread over the SMs), 1: throughput (full tiles)
+
 // 128-row tiles: `units` work items of `rows_per_unit` rows, spread evenly over the waves they need
 static TcChoice choose_tc_tile(long long units, int rows_per_unit, int nsets, int ctas_per_sm = 1)
 {
@@ -1100,6 +1102,11 @@ static TcChoice choose_tc_tile(long long units, int rows_per_unit, int nsets, in
     long long tiles = (units + cap - 1) / cap;
     // Two tiles resident on an SM take turns on its tensor memory: that pays when the work needs more than one
     // wave of full tiles anyway; a call that fits one tile per SM keeps the SMs to itself.
+    // Throughput policy (elo_set_tile_policy(1)): full tiles, as few CTAs as the work needs.  A tile's latency
+    // hardly depends on how many of its 128 rows are in use, so spreading a small call over all SMs (the
+    // default, latency policy) buys a little latency with a lot of SM time -- time that other forwards in
+    // flight on other streams could use.
+    if (g_tile_policy == 1) return TcChoice{cap, (int)tiles};
     int sms = device_info().sm_count;
     if (tiles * nsets > sms) sms *= ctas_per_sm;
     const long long waves = (tiles * nsets + sms - 1) / sms;
@@ -1152,6 +1159,15 @@ static int launch_tc(Kernel kern, const Params& p, dim3 grid, size_t bytes, cuda
 }  // namespace elo
 
 using namespace elo;
+
+extern "C" int elo_set_tile_policy(int policy)
+{
+    if (policy != 0 && policy != 1) return set_error(ELO_ERR_INVALID_ARGUMENT, "elo_set_tile_policy: 0 (latency) or 1 (throughput)");
+    g_tile_policy = policy;
+    return ELO_OK;
+}
+
+extern "C" int elo_get_tile_policy(void) { return g_tile_policy; }
 
 extern "C" int elo_set_time_log(long long* device_buf)
 {

@@ -76,6 +76,14 @@ int elo_fused_conv_random_k(int batch_size, int H, int W, int npoints, int kerne
  * The packed `weights` a descriptor carries must match the engine (packing.pack_stream_tc / pack_stream). */
 int elo_set_mlp_engine(int engine);
 int elo_get_mlp_engine(void);
+/* How the tensor-core kernels cut a call into 128-row tiles (results are identical):
+ *   0 (default)  latency: a call that needs fewer tiles than there are SMs is spread over all of them (fewer
+ *                rows per tile: shorter gather / pooling phases, the shortest single forward);
+ *   1            throughput: full tiles, as few CTAs as the work needs -- less SM time per forward, which is
+ *                what counts when several independent forwards are in flight on different streams.
+ * Read when a forward is launched (or captured into a CUDA graph). */
+int elo_set_tile_policy(int policy);
+int elo_get_tile_policy(void);
 /* Work decomposition of the two stand-alone index ops (results are identical, bit for bit):
  *   0 (default)  by size: calls with at least 2 x 64 queries per SM, K <= 32 and distance^2 < 1e10 take the
  *                tile-staged thread-per-query kernel (fused_conv_tiled.cu), everything else one warp per query;

@@ -267,6 +267,23 @@ def test_dependent_launch_on_and_off_agree(elo, world):
         assert torch.allclose(a, b, rtol=0, atol=1e-6)       # atomics in the re-projection may reorder float adds
 
 
+def test_tile_policies_agree(elo, world):
+    """elo_set_tile_policy only changes how queries are cut into 128-row tiles (full tiles vs spread over the SMs):
+    a row's arithmetic does not depend on its neighbours in the tile, so the forward gives the same numbers."""
+    dev = world["dev"]
+    outs = []
+    try:
+        for policy in (0, 1):
+            elo._lib.set_tile_policy(policy)
+            outs.append(elo.get_model(world["pc"].to(dev), H_IN, W_IN, world["T"].to(dev), None, None, False,
+                                      params=world["store"], perms=world["perms"]))
+            torch.cuda.synchronize()
+    finally:
+        elo._lib.set_tile_policy(0)
+    for a, b in zip(*outs):
+        assert torch.allclose(a, b, rtol=0, atol=1e-6)       # atomics in the re-projection may reorder float adds
+
+
 def test_engine_graph_replay_is_deterministic(elo, world):
     dev = world["dev"]
     eng = elo.PWCLOEngine(2, H_IN, W_IN, NPTS, params=world["store"], perms=world["perms"], device=dev).capture()
