@@ -283,6 +283,7 @@ struct Cv2Params {
     Window g;
     long long total_q;
     int qt, C, total_chunks, nring;
+    int sl_in_ring;      // tensor-core engine: logits staged in the dead weight ring, values pooled straight from X
     const float* xyz1;
     const float* f1;
     const float* cv1;
@@ -578,8 +579,8 @@ constexpr int POOL_LD64 = 65;
 
 // masked softmax over the K rows of a query for one channel, applied to val (TF: where(mask, w, -1e10),
 // softmax(dim=2), reduce_sum(w * val)); an all-masked group gets uniform weights 1/K
-__device__ __forceinline__ float pool_softmax(const float* SL, const float* SV, int ld_v, const int* nbr, int r0, int K,
-                                              int c)
+template <typename ValueAt>
+__device__ __forceinline__ float pool_softmax_v(const float* SL, ValueAt value_at, const int* nbr, int r0, int K, int c)
 {
     // Online form over chunks of 8 rows: a chunk's loads, its exponentials and its sums are independent of each
     // other (K = 4 / 6 / 32 in the model: one chunk is the common case), only the running maximum couples the
@@ -594,7 +595,7 @@ __device__ __forceinline__ float pool_softmax(const float* SL, const float* SV, 
             l[i] = -INFINITY; v[i] = 0.f;
             if (k < K) {
                 l[i] = nbr[r0 + k] >= 0 ? SL[(r0 + k) * POOL_LD64 + c] : -1e10f;
-                v[i] = SV[(r0 + k) * ld_v + c];
+                v[i] = value_at(r0 + k, c);
             }
         }
         float mn = m;
@@ -611,6 +612,12 @@ __device__ __forceinline__ float pool_softmax(const float* SL, const float* SV, 
         m = mn;
     }
     return a / s;
+}
+
+__device__ __forceinline__ float pool_softmax(const float* SL, const float* SV, int ld_v, const int* nbr, int r0, int K,
+                                              int c)
+{
+    return pool_softmax_v(SL, [&](int row, int ch) { return SV[row * ld_v + ch]; }, nbr, r0, K, c);
 }
 
 __global__ void __launch_bounds__(TC_LAUNCH_THREADS, 2) group_mlp_max_tc_kernel(const GroupMlpParams p)
@@ -825,14 +832,14 @@ __global__ void __launch_bounds__(TC_LAUNCH_THREADS, 2) cost_volume_1_tc_kernel(
     pipe.stamp(7);
 }
 
-__global__ void __launch_bounds__(TC_LAUNCH_THREADS, 1) cost_volume_2_tc_kernel(const Cv2Params p)
+__global__ void __launch_bounds__(TC_LAUNCH_THREADS, 2) cost_volume_2_tc_kernel(const Cv2Params p)
 {
     constexpr int RS = TC_ROWS;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int C = p.C;
     // staging channels: [0,10) xyz, [16,16+C) f1, [16+C,80+C) stage-1 features of the neighbour; then the pool
     // staging SV / SL as [row][65]
-    TcSmem sm = tc_carve(smem_raw, p.nring, 0, (size_t)(80 + C + 2 * POOL_LD64) * RS);
+    TcSmem sm = tc_carve(smem_raw, p.nring, 0, (size_t)(80 + C + (p.sl_in_ring ? 0 : 2 * POOL_LD64)) * RS);
     const int warp = threadIdx.x >> 5;
     const Window g = p.g;
     const TcRows rows(g.K);
@@ -882,10 +889,13 @@ __global__ void __launch_bounds__(TC_LAUNCH_THREADS, 1) cost_volume_2_tc_kernel(
     pipe.load_a_from_smem(X, 16, C + 64, 64);
     pipe.signal_a_ready();
     const int m = pipe.my_row();
+    // Pool staging.  sl_in_ring (two tiles per SM): the logits go to the weight ring, dead by the time the last
+    // epilogue writes them, and the values are pooled straight from their place in X (4-way bank conflicts on
+    // K loads per output); otherwise both get a [row][65] copy behind X.
     float* SV = X + (size_t)(80 + C) * RS;
-    float* SL = SV + RS * POOL_LD64;
-    // while the first MMAs run: this row's gathered stage-1 features into the pooling layout (masked rows hold 0)
-    for (int c = pipe.my_half() * 32; c < pipe.my_half() * 32 + 32; ++c) SV[m * POOL_LD64 + c] = X[act_index(16 + C + c, m, RS)];
+    float* SL = p.sl_in_ring ? sm.ring : SV + RS * POOL_LD64;
+    if (!p.sl_in_ring)      // while the first MMAs run: this row's gathered stage-1 features (masked rows hold 0)
+        for (int c = pipe.my_half() * 32; c < pipe.my_half() * 32 + 32; ++c) SV[m * POOL_LD64 + c] = X[act_index(16 + C + c, m, RS)];
     pipe.epilogue<true>(64, [&](int b, const float (&v)[16]) { pipe.store_a(0, b, v); });         // enc
     pipe.signal_a_ready();
     pipe.epilogue<true>(128, [&](int b, const float (&v)[16]) { pipe.store_a(0, b, v); });
@@ -899,7 +909,9 @@ __global__ void __launch_bounds__(TC_LAUNCH_THREADS, 1) cost_volume_2_tc_kernel(
         const int ql = t >> 6, c = t & 63;
         const long long gq = q0 + ql;
         if (gq >= p.total_q) break;
-        p.out[gq * 64 + c] = pool_softmax(SL, SV, POOL_LD64, nbr, rows.row(ql, 0), g.K, c);
+        p.out[gq * 64 + c] = p.sl_in_ring
+            ? pool_softmax_v(SL, [&](int row, int ch) { return X[act_index(16 + C + ch, row, RS)]; }, nbr, rows.row(ql, 0), g.K, c)
+            : pool_softmax(SL, SV, POOL_LD64, nbr, rows.row(ql, 0), g.K, c);
     }
     if (p.dbg_nbr != nullptr)
         for (int r = threadIdx.x; r < RS; r += CTA_THREADS) {
@@ -1131,12 +1143,15 @@ static constexpr int SMEM_HALF = 112 * 1024;
 
 static int g_ring_alone = getenv("ELO_TC_RING") ? atoi(getenv("ELO_TC_RING")) : 3;     // measured: 3..8 slots give the same tile latency
 
+static int g_ring_shared = getenv("ELO_TC_RING_SHARED") ? atoi(getenv("ELO_TC_RING_SHARED")) : 3;
+
 static int tc_pick_ring(size_t base, int total_chunks, bool two_per_sm = false)
 {
     if (two_per_sm) {
         long long n2 = ((long long)SMEM_HALF - (long long)base) / TC_CHUNK_BYTES;
         if (n2 > total_chunks) n2 = total_chunks;
-        if (n2 >= 3 || n2 == total_chunks) return (int)(n2 > MAX_RING ? MAX_RING : n2);
+        if (n2 > g_ring_shared && g_ring_shared >= 2) n2 = g_ring_shared;
+        if (n2 >= 2 || n2 == total_chunks) return (int)(n2 > MAX_RING ? MAX_RING : n2);
     }
     long long n = ((long long)SMEM_LIMIT - (long long)base) / TC_CHUNK_BYTES;
     // a tile that has the SM to itself still leaves room for the small kernels of other forwards in flight
@@ -1333,6 +1348,7 @@ extern "C" int elo_cost_volume_2(const elo_cost_volume_desc* d, void* stream)
     if (d->window_p.K > 64) return set_error(ELO_ERR_UNSUPPORTED, "cost_volume_2: nsample > 64");
     if (d->batch_size == 0) return ELO_OK;
     Cv2Params p;
+    p.sl_in_ring = 0;
     p.qs.H1 = d->H; p.qs.W1 = d->W; p.qs.oh = d->H; p.qs.ow = d->W; p.qs.qs_h = 1; p.qs.qs_w = 1;
     p.g = make_window(&d->window_p);
     p.total_q = (long long)d->batch_size * d->H * d->W;
@@ -1345,10 +1361,15 @@ extern "C" int elo_cost_volume_2(const elo_cost_volume_desc* d, void* stream)
         if (!p.nbr_in) return set_error(ELO_ERR_INVALID_ARGUMENT, "cost_volume_2: the tensor-core engine takes nbr_p from elo_multi_search");
         p.total_chunks = tc_layer_chunks(10, 64) + tc_layer_chunks(128 + d->C, 128) + tc_layer_chunks(128, 64);
         if (p.g.K > 32) return set_error(ELO_ERR_UNSUPPORTED, "cost_volume_2: the tensor-core engine takes nsample <= 32");
-        const size_t base = tc_base_smem(0, (size_t)(80 + d->C + 130) * TC_ROWS);
-        p.nring = tc_pick_ring(base, p.total_chunks);
+        size_t base = tc_base_smem(0, (size_t)(80 + d->C) * TC_ROWS);
+        p.nring = tc_pick_ring(base, p.total_chunks, /*two_per_sm=*/true);
+        p.sl_in_ring = (p.nring >= 3 && base + (size_t)p.nring * TC_CHUNK_BYTES <= (size_t)SMEM_HALF) ? 1 : 0;
+        if (!p.sl_in_ring) {
+            base = tc_base_smem(0, (size_t)(80 + d->C + 2 * POOL_LD64) * TC_ROWS);
+            p.nring = tc_pick_ring(base, p.total_chunks);
+        }
         if (p.nring < 2) return set_error(ELO_ERR_UNSUPPORTED, "cost_volume_2: tile does not fit shared memory");
-        const TcChoice tc = choose_tc_tile(p.total_q, p.g.K, 1);
+        const TcChoice tc = choose_tc_tile(p.total_q, p.g.K, 1, p.sl_in_ring ? 2 : 1);
         p.qt = tc.per_tile;
         p.g.kt = 0;
         return launch_tc(cost_volume_2_tc_kernel, p, dim3(tc.tiles), base + (size_t)p.nring * TC_CHUNK_BYTES,
