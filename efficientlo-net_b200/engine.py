@@ -97,8 +97,17 @@ class PWCLOPipeline:
         self.device = torch.device(device)
         store = params if isinstance(params, ParamStore) else ParamStore(
             params if params is not None else init_params(0), self.device)
-        self.engines = [PWCLOEngine(batch_size, H_input, W_input, num_points, params=store, perms=perms,
-                                    device=device).capture() for _ in range(depth)]
+        # several forwards in flight: full 128-row tiles (least SM time per forward) instead of spreading every
+        # small call over all SMs (shortest single forward); the policy is read when the graphs are captured
+        from . import _lib
+        prev = _lib.lib().elo_get_tile_policy()
+        if streams > 1:
+            _lib.set_tile_policy(1)
+        try:
+            self.engines = [PWCLOEngine(batch_size, H_input, W_input, num_points, params=store, perms=perms,
+                                        device=device).capture() for _ in range(depth)]
+        finally:
+            _lib.set_tile_policy(prev)
         self.copy_stream = torch.cuda.Stream(self.device)
         self.compute_streams = [torch.cuda.Stream(self.device) for _ in range(max(1, streams))]
         self.uploaded = [torch.cuda.Event() for _ in range(depth)]
