@@ -6,7 +6,8 @@ O=gpurun_out/evidence
 mkdir -p $O
 python bench.py > $O/bench.json 2> $O/bench.err
 python bench.py --streams 1 --steps 300 --no-cpu > $O/bench_serial.json 2>> $O/bench.err
-python bench.py --batch 8 --steps 100 --warmup 5 --no-cpu > $O/bench_b8.json 2>> $O/bench.err
+python bench.py --streams 12 --tile-policy 0 --steps 500 --no-cpu > $O/bench_spread.json 2>> $O/bench.err
+python bench.py --batch 8 --streams 4 --steps 100 --warmup 5 --no-cpu > $O/bench_b8.json 2>> $O/bench.err
 python bench.py --impl reference --steps 8 --warmup 1 > $O/bench_ref.json 2>> $O/bench.err
 python tools/index_bench.py 20 > $O/index_bench.jsonl 2>> $O/bench.err
 python tools/train_bench.py --batch 8 --steps 5 > $O/train_b8.json 2> $O/train.err
