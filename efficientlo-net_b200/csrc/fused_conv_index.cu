@@ -15,6 +15,7 @@
 //     (kernel K1) -- and no memset pass is needed.
 #include <cuda_runtime.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include "../../include/elo_b200.h"
 #include "elo_common.cuh"
@@ -187,6 +188,10 @@ int launch_index_tiled(bool select, int B, int H, int W, int N, const Window& g,
                        const int* idx_n2, const int* random_hw, int* out_idx, float* out_valid, float* out_vdis,
                        float* out_mask, cudaStream_t stream, int* rc);
 
+int launch_search_tiled(bool select, int B, int H1, int W1, int oh, int ow, int qs_h, int qs_w, const Window& g,
+                        const float* xyz1, const float* xyz2, const int* random_hw, int* out_nbr, cudaStream_t stream,
+                        int* rc);
+
 static int launch_index(bool select, int B, int H, int W, int N, int kH, int kW, int K, int flag_copy,
                         float distance, int stride_h, int stride_w, const float* xyz1,
                         const float* xyz2, const int* idx_n2, const int* random_hw, int* out_idx,
@@ -285,6 +290,25 @@ extern "C" int elo_multi_search(const elo_search_desc* specs, int nspec, void* s
         if (kt > 5000 || w->K > 5000 || w->small_h >= 32768 || w->small_w >= 32768)
             return set_error(ELO_ERR_UNSUPPORTED, "multi_search: window / K limited to 5000, grids to 32767");
         if (d->batch_size == 0) continue;
+        // Experiment (ELO_SEARCH_TILED=1, off by default): under the throughput tile policy, dense-query searches
+        // with wide windows on the tile-staged thread-per-query kernel (its own launch).  Measured: less SM time
+        // per search, but 10 more launches per forward and long single-search latencies -- 5224 instead of 6409
+        // pairs/s with 12 forwards in flight, which at 42 vs 52 launches per forward is the same ~270 000 kernel
+        // launches per second: that rate, not SM time, bounds the throughput mode.
+        static const bool search_tiled = getenv("ELO_SEARCH_TILED") != nullptr && getenv("ELO_SEARCH_TILED")[0] == '1';
+        if (search_tiled && elo_get_tile_policy() == 1 && kt >= 64 && d->queries.q_stride_h == 1 && d->queries.q_stride_w == 1) {
+            Window gw;
+            gw.h2 = w->small_h; gw.w2 = w->small_w; gw.kH = w->kernel_size_H; gw.kW = w->kernel_size_W; gw.kt = (int)kt;
+            gw.stride_h = w->stride_h; gw.stride_w = w->stride_w; gw.K = w->K; gw.flag_copy = 0;
+            gw.d2max = w->distance * w->distance;
+            int rc = ELO_OK;
+            if (launch_search_tiled(d->select != 0, d->batch_size, d->queries.H, d->queries.W, d->queries.out_h,
+                                    d->queries.out_w, 1, 1, gw, d->xyz1, d->xyz2, w->random_hw, d->out_nbr,
+                                    (cudaStream_t)stream, &rc)) {
+                if (rc != ELO_OK) return rc;
+                continue;
+            }
+        }
         SearchSpec& sp = p.spec[p.nspec++];
         sp.qs.H1 = d->queries.H; sp.qs.W1 = d->queries.W; sp.qs.oh = d->queries.out_h; sp.qs.ow = d->queries.out_w;
         sp.qs.qs_h = d->queries.q_stride_h; sp.qs.qs_w = d->queries.q_stride_w;

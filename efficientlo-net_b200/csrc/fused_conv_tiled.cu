@@ -54,8 +54,11 @@ struct TiledParams {
     Window g;
     const float* xyz1;
     const float* xyz2;
-    const int* idx_n2;
+    const int* idx_n2;   // (B, N, 2) [h, w]; or NULL: the queries are the strided sub-grid `qs` (batched search)
     const int* random_hw;
+    int* out_nbr;        // batched search: (B, N, K) linear cell of the searched grid or -1; then the four
+                         // outputs of the op below are all NULL
+    int qs_ow, qs_h, qs_w;   // sub-grid of the query image: query n -> cell ((n / ow) * qs_h, (n % ow) * qs_w)
     int* out_idx;
     float* out_valid;
     float* out_vdis;
@@ -147,8 +150,13 @@ __global__ void __launch_bounds__(TQ, (KR <= 17 ? 896 / TQ : 512 / TQ)) fused_co
     bool cvalid = false;
     if (active) {
         b = (int)(q / p.N);
-        const int2 hw = __ldg(reinterpret_cast<const int2*>(p.idx_n2) + q);
-        h = hw.x; w = hw.y;
+        if (p.idx_n2 != nullptr) {
+            const int2 hw = __ldg(reinterpret_cast<const int2*>(p.idx_n2) + q);
+            h = hw.x; w = hw.y;
+        } else {
+            const int n = (int)(q - (long long)b * p.N);
+            h = (n / p.qs_ow) * p.qs_h; w = (n % p.qs_ow) * p.qs_w;
+        }
         if (h >= 0 && h < p.H && w >= 0 && w < p.W) {       // reference: out-of-range = UB; here: empty row
             const float* c = p.xyz1 + ((size_t)b * p.H * p.W + (size_t)h * p.W + w) * 3;
             xc = __ldg(c); yc = __ldg(c + 1); zc = __ldg(c + 2);
@@ -562,7 +570,17 @@ __global__ void __launch_bounds__(TQ, (KR <= 17 ? 896 / TQ : 512 / TQ)) fused_co
         else if (bc & 1) { pk = s_first[r]; on = true; }
         vb = on ? (bc >> 1) : 0; vh = pk >> 16; vw = pk & 0xffff; vm = on ? 1.0f : 0.0f;
     };
-    if (nrows > 0) {
+    if (nrows > 0 && p.out_nbr != nullptr) {
+        // batched-search form: one int per slot, the warp's 32 rows are contiguous
+        int* o_nbr = p.out_nbr + (q0 + r_lo) * K;
+        const unsigned nslots = (unsigned)nrows * K;
+        for (unsigned sl = lane; sl < nslots; sl += 32) {
+            int vb, vh, vw; float vm;
+            slot_value(sl, vb, vh, vw, vm);
+            o_nbr[sl] = vm != 0.f ? vh * g.w2 + vw : -1;
+        }
+    }
+    if (nrows > 0 && p.out_idx != nullptr) {
         int* o_idx = p.out_idx + (q0 + r_lo) * K * 3;
         float* o_mask = p.out_mask + (q0 + r_lo) * K;
         const unsigned nslots = (unsigned)nrows * K;
@@ -605,12 +623,20 @@ __global__ void __launch_bounds__(TQ, (KR <= 17 ? 896 / TQ : 512 / TQ)) fused_co
                 const int qt = s_ties[t];
                 const long long gq = q0 + qt;
                 const int bq = (int)(gq / p.N);
-                const int2 hwq = __ldg(reinterpret_cast<const int2*>(p.idx_n2) + gq);
+                int2 hwq;
+                if (p.idx_n2 != nullptr) {
+                    hwq = __ldg(reinterpret_cast<const int2*>(p.idx_n2) + gq);
+                } else {
+                    const int n = (int)(gq - (long long)bq * p.N);
+                    hwq = make_int2((n / p.qs_ow) * p.qs_h, (n % p.qs_ow) * p.qs_w);
+                }
                 const float* c = p.xyz1 + ((size_t)bq * p.H * p.W + (size_t)hwq.x * p.W + hwq.y) * 3;
                 const float* g2q = p.xyz2 + (size_t)bq * g.h2 * g.w2 * 3;
-                int* o_idx = p.out_idx + gq * K * 3;
-                float* o_mask = p.out_mask + gq * K;
+                int* o_idx = p.out_idx ? p.out_idx + gq * K * 3 : nullptr;
+                float* o_mask = p.out_mask ? p.out_mask + gq * K : nullptr;
+                int* o_nbr = p.out_nbr ? p.out_nbr + gq * K : nullptr;
                 auto emit = [&](int slot, int hh, int ww) {
+                    if (o_nbr != nullptr) { o_nbr[slot] = hh * g.w2 + ww; return; }
                     o_idx[slot * 3] = bq; o_idx[slot * 3 + 1] = hh; o_idx[slot * 3 + 2] = ww;
                     o_mask[slot] = 1.0f;
                 };
@@ -621,6 +647,7 @@ __global__ void __launch_bounds__(TQ, (KR <= 17 ? 896 / TQ : 512 / TQ)) fused_co
                 // slots the replay did not emit: zero, or the duplicate of entry 0 (flag_copy)
                 const bool copy = g.flag_copy == 1;
                 for (int k = written + lane; k < K; k += 32) {
+                    if (o_nbr != nullptr) { o_nbr[k] = -1; continue; }
                     o_idx[k * 3] = copy ? bq : 0;
                     o_idx[k * 3 + 1] = copy ? sc.first >> 16 : 0;
                     o_idx[k * 3 + 2] = copy ? sc.first & 0xffff : 0;
@@ -672,29 +699,14 @@ static size_t tiled_smem(const Window& g, bool select, int tq, int* tile_cap, in
     return 2 * up((size_t)g.kt * 4) + up((size_t)std::max(g.K, QG) * tq * 4) + 6 * up((size_t)tq * 4) + up(64) + (size_t)*tile_bytes;
 }
 
-// Returns 1 when the tiled kernel took the call (status in *rc), 0 when the caller should use the
-// warp-per-query kernel (few queries, K > 32, distance^2 >= 1e10, window too large for shared memory).
-int launch_index_tiled(bool select, int B, int H, int W, int N, const Window& g, const float* xyz1, const float* xyz2,
-                       const int* idx_n2, const int* random_hw, int* out_idx, float* out_valid, float* out_vdis,
-                       float* out_mask, cudaStream_t stream, int* rc)
+// Everything of TiledParams that follows from the window: key layout, writer constants, the centre-out walk.
+static void tiled_prepare(TiledParams& p, bool select)
 {
-    const long long total = (long long)B * N;
-    const DeviceInfo& dev = device_info();
-    const int force = g_index_kernel.load(std::memory_order_relaxed);
-    if (force == 2) return 0;
-    if (g.K > 32 || !(g.d2max < 1e10f)) return 0;
-    if (force != 1 && total < (long long)dev.sm_count * 128 * 2) return 0;   // too few threads to fill the chip
-    if (select && g.kt > MAX_WALK) return 0;
-
-    TiledParams p;
-    p.B = B; p.H = H; p.W = W; p.N = N; p.g = g;
-    p.xyz1 = xyz1; p.xyz2 = xyz2; p.idx_n2 = idx_n2; p.random_hw = random_hw;
-    p.out_idx = out_idx; p.out_valid = out_valid; p.out_vdis = out_vdis; p.out_mask = out_mask;
-    p.total = total;
+    const Window& g = p.g;
     p.jbits = 4;
     while ((1 << p.jbits) < g.kt) ++p.jbits;
     auto aligned = [](const void* q) { return q == nullptr || (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
-    p.vec_ok = aligned(out_idx) && aligned(out_valid) && aligned(out_vdis) && aligned(out_mask) ? 1 : 0;
+    p.vec_ok = aligned(p.out_idx) && aligned(p.out_valid) && aligned(p.out_vdis) && aligned(p.out_mask) ? 1 : 0;
     p.magic_kt = magic_of((unsigned)g.kt);
     p.magic_k = magic_of((unsigned)g.K);
     if (select) {
@@ -712,12 +724,53 @@ int launch_index_tiled(bool select, int B, int H, int W, int N, const Window& g,
             p.walk[j] = ((c / g.kW - hh2) << 16) | ((c % g.kW - hw2) & 0xffff);
         }
     }
+}
+
+// The part that depends on the CTA size, then the launch.
+static cudaError_t tiled_launch(TiledParams& p, bool select, int tq, cudaStream_t stream)
+{
+    const Window& g = p.g;
+    const size_t smem = tiled_smem(g, select, tq, &p.tile_cap, &p.tile_bytes);
+    p.pitch = tq + g.kW;
+    p.near_bound = sqrtf(g.d2max / 12.5f);
+    if (select) {
+        const int hh2 = g.kH / 2, hw2 = g.kW / 2;
+        for (int j = 0; j < g.kt; ++j) {
+            const int dh = p.walk[j] >> 16, dw = (int)(short)(p.walk[j] & 0xffff);
+            p.walk_to[j] = ((dh + hh2) * p.pitch + (dw + hw2)) * 16;
+        }
+    }
+    if (tq == 128) return launch_tiled_tq<128>(select, p, smem, stream);
+    if (tq == 160) return launch_tiled_tq<160>(select, p, smem, stream);
+    return launch_tiled_tq<192>(select, p, smem, stream);
+}
+
+// Returns 1 when the tiled kernel took the call (status in *rc), 0 when the caller should use the
+// warp-per-query kernel (few queries, K > 32, distance^2 >= 1e10, window too large for shared memory).
+int launch_index_tiled(bool select, int B, int H, int W, int N, const Window& g, const float* xyz1, const float* xyz2,
+                       const int* idx_n2, const int* random_hw, int* out_idx, float* out_valid, float* out_vdis,
+                       float* out_mask, cudaStream_t stream, int* rc)
+{
+    const long long total = (long long)B * N;
+    const DeviceInfo& dev = device_info();
+    const int force = g_index_kernel.load(std::memory_order_relaxed);
+    if (force == 2) return 0;
+    if (g.K > 32 || !(g.d2max < 1e10f)) return 0;
+    if (force != 1 && total < (long long)dev.sm_count * 128 * 2) return 0;   // too few threads to fill the chip
+    if (select && g.kt > MAX_WALK) return 0;
+
+    TiledParams p;
+    p.B = B; p.H = H; p.W = W; p.N = N; p.g = g;
+    p.xyz1 = xyz1; p.xyz2 = xyz2; p.idx_n2 = idx_n2; p.random_hw = random_hw;
+    p.out_nbr = nullptr; p.qs_ow = 1; p.qs_h = 1; p.qs_w = 1;
+    p.out_idx = out_idx; p.out_valid = out_valid; p.out_vdis = out_vdis; p.out_mask = out_mask;
+    p.total = total;
+    tiled_prepare(p, select);
 
     // CTA size: the candidate whose CTAs all fit on the chip at once and load the SMs most evenly
     const int regs_cta_limit = (select && g.K > 16) ? 512 : 896;     // threads per SM the register budget allows
     int best_tq = 0;
     double best_cost = 0.0;
-    size_t best_smem = 0;
     for (int tq : {128, 160, 192}) {
         int cap, tb;
         const size_t smem = tiled_smem(g, select, tq, &cap, &tb);
@@ -728,26 +781,35 @@ int launch_index_tiled(bool select, int B, int H, int W, int N, const Window& g,
         const long long rounds = (ctas + dev.sm_count - 1) / dev.sm_count;     // CTAs the busiest SM runs
         double cost = (double)rounds * tq;                                      // queries on the busiest SM
         if (ctas > per_sm * dev.sm_count) cost *= 1.25;                         // a second wave starts late
-        if (best_tq == 0 || cost < best_cost) { best_tq = tq; best_cost = cost; best_smem = smem; }
+        if (best_tq == 0 || cost < best_cost) { best_tq = tq; best_cost = cost; }
     }
     if (best_tq == 0) return 0;
-    tiled_smem(g, select, best_tq, &p.tile_cap, &p.tile_bytes);
-    p.pitch = best_tq + g.kW;
-    p.near_bound = sqrtf(g.d2max / 12.5f);
-    if (select) {
-        const int hh2 = g.kH / 2, hw2 = g.kW / 2;
-        for (int j = 0; j < g.kt; ++j) {
-            const int dh = p.walk[j] >> 16, dw = (int)(short)(p.walk[j] & 0xffff);
-            p.walk_to[j] = ((dh + hh2) * p.pitch + (dw + hw2)) * 16;
-        }
-    }
-
-    cudaError_t err;
-    if (best_tq == 128) err = launch_tiled_tq<128>(select, p, best_smem, stream);
-    else if (best_tq == 160) err = launch_tiled_tq<160>(select, p, best_smem, stream);
-    else err = launch_tiled_tq<192>(select, p, best_smem, stream);
+    const cudaError_t err = tiled_launch(p, select, best_tq, stream);
     *rc = err == cudaSuccess ? ELO_OK : set_cuda_error(err, select ? "fused_conv_select_k (tiled) launch"
                                                                   : "fused_conv_random_k (tiled) launch");
+    return 1;
+}
+
+// One search of elo_multi_search (dense query grid, compact (B, N, K) neighbour table out) on the tiled kernel:
+// a quarter of the warp-per-query kernel's SM time for the wide windows, at a longer latency (128 queries per
+// CTA, one thread each) -- what the throughput tile policy wants.  Returns 1 when it took the search.
+int launch_search_tiled(bool select, int B, int H1, int W1, int oh, int ow, int qs_h, int qs_w, const Window& g,
+                        const float* xyz1, const float* xyz2, const int* random_hw, int* out_nbr, cudaStream_t stream,
+                        int* rc)
+{
+    if (g.K > 32 || !(g.d2max < 1e10f) || (select && g.kt > MAX_WALK)) return 0;
+    int cap, tb;
+    if (tiled_smem(g, select, 128, &cap, &tb) > 100 * 1024) return 0;
+    TiledParams p;
+    p.B = B; p.H = H1; p.W = W1; p.N = oh * ow; p.g = g;
+    p.g.flag_copy = 0;
+    p.xyz1 = xyz1; p.xyz2 = xyz2; p.idx_n2 = nullptr; p.random_hw = random_hw;
+    p.out_nbr = out_nbr; p.qs_ow = ow; p.qs_h = qs_h; p.qs_w = qs_w;
+    p.out_idx = nullptr; p.out_valid = nullptr; p.out_vdis = nullptr; p.out_mask = nullptr;
+    p.total = (long long)B * p.N;
+    tiled_prepare(p, select);
+    const cudaError_t err = tiled_launch(p, select, 128, stream);
+    *rc = err == cudaSuccess ? ELO_OK : set_cuda_error(err, "multi_search (tiled) launch");
     return 1;
 }
 
