@@ -63,7 +63,7 @@ class ProjectDesc(ctypes.Structure):
                 ("inner_batch", _c_int), ("outer_stride", _c_ll), ("feat", _c_void_p),
                 ("T", _c_void_p), ("q", _c_void_p), ("t", _c_void_p),
                 ("pi", _c_float), ("az_res", _c_float), ("v_res", _c_float), ("v_off", _c_float),
-                ("cellmin", _c_void_p), ("out_xyz", _c_void_p), ("out_feat", _c_void_p), ("out_points", _c_void_p),
+                ("cellmin", _c_void_p), ("state", _c_void_p), ("out_xyz", _c_void_p), ("out_feat", _c_void_p), ("out_points", _c_void_p),
                 ("T_apply", _c_void_p), ("out_cell", _c_void_p)]
 
 

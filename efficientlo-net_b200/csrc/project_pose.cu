@@ -12,6 +12,8 @@
 // a bin or a range winner is therefore written with explicit round-to-nearest intrinsics in the
 // reference's operation order, which makes the integer outcomes (cells, winners) reproducible.
 #include <cuda_runtime.h>
+
+#include <algorithm>
 #include <stdint.h>
 #include <stdlib.h>
 #include <math.h>
@@ -27,7 +29,8 @@ struct ProjParams {
     const float* feat;
     const float* T; const int* T_apply; const float* q; const float* t;
     float pi, az, vres, voff;
-    unsigned* cellmin;
+    unsigned long long* cellmin;   // (B,H,W): (~epoch << 32) | range bits of the nearest point seen in this epoch
+    unsigned* state;               // [0] epoch of the current call, [1] CTAs of the scatter kernel that are done
     float* out_xyz; float* out_feat; float* out_points;
     int* out_cell;       // optional (B, N): cell of the point if it is (one of) the nearest of its cell, else -1
 };
@@ -104,26 +107,31 @@ __device__ __forceinline__ int bin_point(const ProjParams& p, float x, float y, 
     return row * p.W + col;
 }
 
-__global__ void project_init_kernel(const ProjParams p)
+// Cell minima carry the call's epoch in their high word ((~epoch) << 32 | range bits): a value left by an
+// earlier call is larger than anything this call writes, so the table never has to be cleared -- the separate
+// initialisation launch is gone (the binning kernel also zeroes the images the scatter adds into).  The epoch
+// lives in device memory (state[0]) and is advanced by the last CTA of the scatter kernel, which keeps a captured
+// CUDA graph replayable.
+__device__ __forceinline__ unsigned long long cell_key(unsigned epoch, unsigned rbits)
 {
-    pdl_trigger();
-    pdl_wait();          // the output images may alias memory an earlier kernel is still reading
-    const long long cells = (long long)p.B * p.H * p.W;
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long stride = (long long)gridDim.x * blockDim.x;
-    for (long long c = i; c < cells; c += stride) p.cellmin[c] = 0xffffffffu;
-    for (long long c = i; c < cells * 3; c += stride) p.out_xyz[c] = 0.f;
-    if (p.out_feat != nullptr)
-        for (long long c = i; c < cells * p.C; c += stride) p.out_feat[c] = 0.f;
+    return ((unsigned long long)(~epoch) << 32) | rbits;
 }
 
 __global__ void project_bin_kernel(const ProjParams p)
 {
     pdl_trigger();
-    pdl_wait();
+    pdl_wait();          // inputs come from earlier kernels; the output images may alias memory they still read
+    const unsigned epoch = *reinterpret_cast<volatile unsigned*>(p.state);
     const long long total = (long long)p.B * p.N;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-         i += (long long)gridDim.x * blockDim.x) {
+    const long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    {
+        const long long cells = (long long)p.B * p.H * p.W;
+        for (long long c = i0; c < cells * 3; c += stride) p.out_xyz[c] = 0.f;
+        if (p.out_feat != nullptr)
+            for (long long c = i0; c < cells * p.C; c += stride) p.out_feat[c] = 0.f;
+    }
+    for (long long i = i0; i < total; i += stride) {
         const int b = (int)(i / p.N), n = (int)(i % p.N);
         float x, y, z, r;
         transform_point(p, b, n, x, y, z);
@@ -131,10 +139,10 @@ __global__ void project_bin_kernel(const ProjParams p)
         // r >= 0 (or NaN, which orders above every finite value as an unsigned pattern).  Zero-padded /
         // cropped points all fall into ONE cell per sample with r = 0, the smallest possible key: a plain
         // store is enough for them and avoids ~10^5 serialised atomics on a single address.
-        unsigned* slot = p.cellmin + (size_t)b * p.H * p.W + cell;
-        const unsigned key = __float_as_uint(r);
-        if (key == 0u) *slot = 0u;
-        else atomicMin(slot, key);
+        unsigned long long* slot = p.cellmin + (size_t)b * p.H * p.W + cell;
+        const unsigned rbits = __float_as_uint(r);
+        if (rbits == 0u) *slot = cell_key(epoch, 0u);
+        else atomicMin(slot, cell_key(epoch, rbits));
         if (p.out_points != nullptr) {
             float* o = p.out_points + (size_t)i * 3;
             o[0] = x; o[1] = y; o[2] = z;
@@ -147,6 +155,7 @@ __global__ void project_scatter_kernel(const ProjParams p)
 {
     pdl_trigger();
     pdl_wait();
+    const unsigned epoch = *reinterpret_cast<volatile unsigned*>(p.state);
     const int slabs = 1 + (p.out_feat != nullptr ? (p.C + 3) / 4 : 0);
     const long long total = (long long)p.B * p.N * slabs;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
@@ -158,7 +167,7 @@ __global__ void project_scatter_kernel(const ProjParams p)
         transform_point(p, b, n, x, y, z);
         const int cell = bin_point(p, x, y, z, r);
         const size_t gcell = (size_t)b * p.H * p.W + cell;
-        const bool winner = __float_as_uint(r) == p.cellmin[gcell];
+        const bool winner = cell_key(epoch, __float_as_uint(r)) == p.cellmin[gcell];
         if (slab == 0 && p.out_cell != nullptr) p.out_cell[pt] = winner ? cell : -1;
         if (!winner) continue;                                       // not the (a) nearest point of its cell
         if (slab == 0) {
@@ -173,6 +182,16 @@ __global__ void project_scatter_kernel(const ProjParams p)
                 const float v = __ldg(f + c);
                 if (v != 0.f) atomicAdd(p.out_feat + gcell * p.C + c, v);
             }
+        }
+    }
+    // every CTA has read the epoch by now: the last one to finish advances it for the next call on this table
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(p.state + 1, 1u) == gridDim.x - 1) {
+            p.state[1] = 0u;
+            p.state[0] = epoch + 1u;
+            __threadfence();
         }
     }
 }
@@ -460,7 +479,7 @@ extern "C" int elo_gt_pose(int batch_size, const float* T_gt, const float* T_tra
 extern "C" int elo_project(const elo_project_desc* d, void* stream)
 {
     if (d == nullptr) return set_error(ELO_ERR_INVALID_ARGUMENT, "project: null descriptor");
-    if (d->batch_size < 0 || d->num_points <= 0 || d->H <= 1 || d->W <= 0 || !d->points || !d->cellmin || !d->out_xyz ||
+    if (d->batch_size < 0 || d->num_points <= 0 || d->H <= 1 || d->W <= 0 || !d->points || !d->cellmin || !d->state || !d->out_xyz ||
         d->mode < 0 || d->mode > 2 || d->point_stride < 3 || (d->feat != nullptr && (d->C <= 0 || !d->out_feat)) ||
         (d->mode == 2 && (!d->q || !d->t)))
         return set_error(ELO_ERR_INVALID_ARGUMENT, "project: bad arguments");
@@ -471,7 +490,7 @@ extern "C" int elo_project(const elo_project_desc* d, void* stream)
     p.inner_batch = d->inner_batch; p.outer_stride = d->outer_stride;
     p.feat = d->feat; p.T = d->T; p.T_apply = d->T_apply; p.q = d->q; p.t = d->t;
     p.pi = d->pi; p.az = d->az_res; p.vres = d->v_res; p.voff = d->v_off;
-    p.cellmin = d->cellmin; p.out_xyz = d->out_xyz; p.out_feat = d->feat ? d->out_feat : nullptr;
+    p.cellmin = d->cellmin; p.state = d->state; p.out_xyz = d->out_xyz; p.out_feat = d->feat ? d->out_feat : nullptr;
     p.out_points = d->out_points;
     p.out_cell = d->out_cell;
     cudaStream_t st = (cudaStream_t)stream;
@@ -482,8 +501,8 @@ extern "C" int elo_project(const elo_project_desc* d, void* stream)
         return (unsigned)(b < 1 ? 1 : (b > cap ? cap : b));
     };
     const long long cells = (long long)p.B * p.H * p.W;
-    cudaError_t err = launch(project_init_kernel, dim3(blocks(cells * (p.C > 3 ? p.C : 3))), dim3(256), 0, st, p);
-    if (err == cudaSuccess) err = launch(project_bin_kernel, dim3(blocks((long long)p.B * p.N)), dim3(256), 0, st, p);
+    const long long bin_work = std::max((long long)p.B * p.N, cells * (p.C > 3 ? p.C : 3));   // points, and image zeroing
+    cudaError_t err = launch(project_bin_kernel, dim3(blocks(bin_work)), dim3(256), 0, st, p);
     const int slabs = 1 + (p.out_feat ? (p.C + 3) / 4 : 0);
     if (err == cudaSuccess)
         err = launch(project_scatter_kernel, dim3(blocks((long long)p.B * p.N * slabs)), dim3(256), 0, st, p);

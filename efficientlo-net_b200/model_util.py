@@ -98,7 +98,9 @@ def project_points(PC, Feature, H_input, W_input, mode=0, T=None, q=None, t=None
     B = PC.shape[0] if batch_size is None else batch_size
     N = PC.shape[1]
     dev = PC.device
-    cellmin = _scratch("cellmin", (B, H_input, W_input), torch.int32, dev)
+    # epoch-tagged cell minima + (epoch, done-counter): persistent per (store scratch name space, image shape)
+    cellmin = _scratch("cellmin64", (B, H_input, W_input), torch.int64, dev, fill=-1)
+    state = _scratch("project_state_%dx%dx%d" % (B, H_input, W_input), (2,), torch.int32, dev, fill=0)
     out_xyz = torch.empty((B, H_input, W_input, 3), dtype=torch.float32, device=dev)
     out_feat = out_pts = None
     d = _lib.ProjectDesc()
@@ -116,7 +118,7 @@ def project_points(PC, Feature, H_input, W_input, mode=0, T=None, q=None, t=None
         T_apply = T_apply.to(device=dev, dtype=torch.int32).contiguous()
         d.T_apply = T_apply.data_ptr()
     d.pi, d.az_res, d.v_res, d.v_off = projection_constants(H_input, W_input)
-    d.cellmin, d.out_xyz = cellmin.data_ptr(), out_xyz.data_ptr()
+    d.cellmin, d.state, d.out_xyz = cellmin.data_ptr(), state.data_ptr(), out_xyz.data_ptr()
     if want_points:
         out_pts = torch.empty((B, N, 3), dtype=torch.float32, device=dev)
         d.out_points = out_pts.data_ptr()

@@ -213,7 +213,10 @@ int elo_set_conv_small(const elo_group_mlp_desc *desc, void *stream);
  * per-sample q (B,4) (w,x,y,z) and t (B,3), empty points stay empty.  Per cell the nearest point
  * wins (equal ranges accumulate); out_xyz (B,H,W,3), out_feat (B,H,W,C) are fully written.
  * points: sample b, point n at points + b*batch_stride + n*point_stride (floats) -- lets the kernel
- * read xyz straight out of the reference's (B, 2N, 6) input.  cellmin: (B,H,W) uint32 scratch. */
+ * read xyz straight out of the reference's (B, 2N, 6) input.
+ * cellmin: (B,H,W) uint64 scratch, all ones before the first call; state: 2 x uint32, zero before the first call.
+ * Both persist between calls on the same images (an epoch in state[0] tags the minima, so nothing is cleared);
+ * calls that may overlap on different streams need their own pair. */
 typedef struct {
     int batch_size, num_points, H, W, C, mode;
     const float *points;
@@ -224,7 +227,8 @@ typedef struct {
     const float *feat;        /* (B, num_points, C) or NULL */
     const float *T, *q, *t;
     float pi, az_res, v_res, v_off;   /* fp32 constants of model_util.py:204-210 */
-    unsigned *cellmin;
+    unsigned long long *cellmin;
+    unsigned *state;
     float *out_xyz, *out_feat;
     float *out_points;        /* optional (B, num_points, 3): the transformed points */
     const int *T_apply;       /* optional (B): mode 1 multiplies sample b by T[b] only if T_apply[b] != 0 */
