@@ -292,9 +292,8 @@ extern "C" int elo_multi_search(const elo_search_desc* specs, int nspec, void* s
         if (d->batch_size == 0) continue;
         // Experiment (ELO_SEARCH_TILED=1, off by default): under the throughput tile policy, dense-query searches
         // with wide windows on the tile-staged thread-per-query kernel (its own launch).  Measured: less SM time
-        // per search, but 10 more launches per forward and long single-search latencies -- 5224 instead of 6409
-        // pairs/s with 12 forwards in flight, which at 42 vs 52 launches per forward is the same ~270 000 kernel
-        // launches per second: that rate, not SM time, bounds the throughput mode.
+        // per search, but 10 more launches per forward and 25-40 us single-search latencies that stretch a forward
+        // from 0.54 to 0.78 ms -- 5224 instead of 6409 pairs/s with 12 forwards in flight.
         static const bool search_tiled = getenv("ELO_SEARCH_TILED") != nullptr && getenv("ELO_SEARCH_TILED")[0] == '1';
         if (search_tiled && elo_get_tile_policy() == 1 && kt >= 64 && d->queries.q_stride_h == 1 && d->queries.q_stride_w == 1) {
             Window gw;
