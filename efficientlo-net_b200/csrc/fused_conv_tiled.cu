@@ -320,18 +320,29 @@ __global__ void __launch_bounds__(TQ, (KR <= 17 ? 896 / TQ : 512 / TQ)) fused_co
             float4* t4 = reinterpret_cast<float4*>(tile);
             int c0 = tg.col0 % g.w2;
             if (c0 < 0) c0 += g.w2;
+            // a column of the tile per thread; its rows in groups of SR whose loads are all issued before any of
+            // them is used (a plain row loop would pay one L2 round trip per row)
+            constexpr int SR = 8;
             for (int c = tid; c < tg.tw; c += TQ) {
                 const int gc = (c0 + c) % g.w2;
-                for (int r = 0; r < tg.th; ++r) {
-                    const int gr = tg.row0 + r;
-                    float x = 0.f, y = 0.f, z = 0.f;
-                    if (gr >= 0 && gr < g.h2) {
-                        const float* s = g2 + ((size_t)gr * g.w2 + gc) * 3;
-                        x = __ldg(s); y = __ldg(s + 1); z = __ldg(s + 2);
+                for (int r0 = 0; r0 < tg.th; r0 += SR) {
+                    float x[SR], y[SR], z[SR];
+#pragma unroll
+                    for (int i = 0; i < SR; ++i) {
+                        const int gr = tg.row0 + r0 + i;
+                        x[i] = y[i] = z[i] = 0.f;
+                        if (r0 + i < tg.th && gr >= 0 && gr < g.h2) {
+                            const float* s = g2 + ((size_t)gr * g.w2 + gc) * 3;
+                            x[i] = __ldg(s); y[i] = __ldg(s + 1); z[i] = __ldg(s + 2);
+                        }
                     }
-                    // empty pixel (reference :98-104); FSETP.GTU there: a NaN pixel counts as a point
-                    t4[r * pitch + c] = make_float4(x, y, z, sq3(x, y, z) <= 1e-10f ? 1.0f : 0.0f);
-                    far = far || !(fmaxf(fmaxf(fabsf(x), fabsf(y)), fabsf(z)) <= p.near_bound);
+#pragma unroll
+                    for (int i = 0; i < SR; ++i) {
+                        if (r0 + i >= tg.th) continue;
+                        // empty pixel (reference :98-104); FSETP.GTU there: a NaN pixel counts as a point
+                        t4[(r0 + i) * pitch + c] = make_float4(x[i], y[i], z[i], sq3(x[i], y[i], z[i]) <= 1e-10f ? 1.0f : 0.0f);
+                        far = far || !(fmaxf(fmaxf(fabsf(x[i]), fabsf(y[i])), fabsf(z[i])) <= p.near_bound);
+                    }
                 }
             }
         }
