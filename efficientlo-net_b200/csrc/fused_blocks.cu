@@ -1211,6 +1211,14 @@ extern "C" int elo_group_mlp_max(const elo_group_mlp_desc* d, void* stream)
     for (int l = 0; l < d->num_layers; ++l)
         if (!width_ok(d->cout[l])) return set_error(ELO_ERR_UNSUPPORTED, "group_mlp_max: layer widths must be 64 or 128");
     if (d->window[0].K > 64) return set_error(ELO_ERR_UNSUPPORTED, "group_mlp_max: K > 64");
+    if (d->nsets == 2) {
+        // the two sets of a launch share ONE window geometry (only the scan order, features and weights differ)
+        const elo_window &a = d->window[0], &b = d->window[1];
+        if (a.kernel_size_H != b.kernel_size_H || a.kernel_size_W != b.kernel_size_W || a.K != b.K ||
+            a.distance != b.distance || a.stride_h != b.stride_h || a.stride_w != b.stride_w ||
+            a.small_h != b.small_h || a.small_w != b.small_w)
+            return set_error(ELO_ERR_INVALID_ARGUMENT, "group_mlp_max: window[1] differs from window[0] in geometry");
+    }
     if (d->batch_size == 0) return ELO_OK;
 
     GroupMlpParams p;

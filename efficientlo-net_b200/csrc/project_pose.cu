@@ -185,14 +185,27 @@ __global__ void project_scatter_kernel(const ProjParams p)
         }
     }
     // every CTA has read the epoch by now: the last one to finish advances it for the next call on this table
+    __shared__ bool s_last_cta;
     __syncthreads();
     if (threadIdx.x == 0) {
         __threadfence();
-        if (atomicAdd(p.state + 1, 1u) == gridDim.x - 1) {
-            p.state[1] = 0u;
-            p.state[0] = epoch + 1u;
-            __threadfence();
-        }
+        s_last_cta = atomicAdd(p.state + 1, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (!s_last_cta) return;
+    // The 32-bit epoch wraps after 2^32 calls on one table; keys of epoch 0 (high word ~0) would then lose against
+    // every stale minimum.  On the wrapping call the last CTA -- every other CTA is done with the table -- refills
+    // it with all ones, the state a fresh table starts from.
+    if (epoch + 1u == 0u) {
+        const long long cells = (long long)p.B * p.H * p.W;
+        for (long long c = threadIdx.x; c < cells; c += blockDim.x) p.cellmin[c] = ~0ull;
+        __threadfence();
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        p.state[1] = 0u;
+        p.state[0] = epoch + 1u;
+        __threadfence();
     }
 }
 

@@ -4,8 +4,8 @@ Frame pairs are independent at inference, so the path is data-parallel over pair
 the data path (batch-shard first).  torch.distributed (NCCL on GPUs, gloo in the
 CPU tests) is used only around it: to agree on the shard boundaries, to reduce timings with MAX, and to
 gather the regressed poses of all shards in order for evaluation.
-Row-band sharding of a single pair with a halo exchange per level is not implemented in this round
-(DESIGN.md section 7 says why it does not pay at 64x1800).
+Row-band sharding of a single pair (one halo exchange per pyramid level) lives in rowband.py; DESIGN.md
+section 7 says where it pays (128x2048) and where it does not (64x1800).
 """
 import torch
 import torch.distributed as dist

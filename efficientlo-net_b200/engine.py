@@ -12,16 +12,33 @@ from .params import init_params, make_perms
 from .store import ParamStore
 
 
+def _order_after_producer(stream, device, *tensors):
+    """Device-resident inputs were produced on the caller's current stream: the copy on `stream` must wait for it,
+    and the caching allocator must not recycle them while that copy is in flight."""
+    cuda = [t for t in tensors if t is not None and t.is_cuda]
+    if not cuda:
+        return
+    stream.wait_stream(torch.cuda.current_stream(device))
+    for t in cuda:
+        t.record_stream(stream)
+
+
 class PWCLOEngine:
     def __init__(self, batch_size, H_input=64, W_input=1800, num_points=150000, params=None, perms=None,
-                 device="cuda:0", use_graph=True):
+                 device="cuda:0", use_graph=True, packed=False):
+        """packed=False: the static input buffer has the reference's placeholder shape (B, 2N, 6) (pwclo_model.py:19).
+        packed=True: it is (B, 2N, 3) -- xyz only, the 12 of 24 bytes per point the path reads -- and load() also
+        accepts the two frames as (B, n1, 3) / (B, n2, 3) prefixes without their zero padding (the padding is done on
+        the device: rows past the prefix stay, or are reset to, zero)."""
         self.B, self.H, self.W, self.N = batch_size, H_input, W_input, num_points
+        self.packed = bool(packed)
+        self.filled = [0, 0]          # rows of each frame's slab that may hold points (packed prefix uploads)
         self.device = torch.device(device)
         self.store = params if isinstance(params, ParamStore) else ParamStore(
             params if params is not None else init_params(0), self.device)
         self.perms = perms if perms is not None else make_perms(0)
         self.perms = {k: v.to(self.device) for k, v in self.perms.items()}
-        self.pc = torch.zeros(batch_size, 2 * num_points, 6, device=self.device)
+        self.pc = torch.zeros(batch_size, 2 * num_points, 3 if self.packed else 6, device=self.device)
         self.T_gt = torch.eye(4, device=self.device).expand(batch_size, 4, 4).contiguous()
         self.use_graph = use_graph
         self.graph = None
@@ -53,10 +70,34 @@ class PWCLOEngine:
             torch.cuda.synchronize(self.device)
         return self
 
-    def load(self, point_cloud, T_gt=None, non_blocking=True):
-        """Stage one batch: (B, 2N, 6) host (ideally pinned) or device tensor -> static device buffer."""
-        with torch.cuda.stream(self.stream):
-            self.pc.copy_(point_cloud, non_blocking=non_blocking)
+    def load(self, point_cloud, T_gt=None, non_blocking=True, stream=None):
+        """Stage one batch into the static device buffer, on the engine's stream (or `stream`).
+        point_cloud: a (B, 2N, 6) tensor (or (B, 2N, 3) for a packed engine), host (ideally pinned) or device; or, for
+        a packed engine, a pair (xyz_f1 (B, n1, 3), xyz_f2 (B, n2, 3)) with n1, n2 <= N: only the rows that hold
+        points travel, the zero padding of main.py:327-333 / kitti_dataset.py:76-80 happens here on the device."""
+        stream = stream if stream is not None else self.stream
+        frames = point_cloud if isinstance(point_cloud, (tuple, list)) else None
+        _order_after_producer(stream, self.device, *(frames if frames is not None else (point_cloud,)), T_gt)
+        with torch.cuda.stream(stream):
+            if frames is None:
+                if point_cloud.shape[-1] != self.pc.shape[-1]:
+                    raise ValueError("this engine takes (B, 2N, %d) clouds%s" % (
+                        self.pc.shape[-1], " or a pair of (B, n, 3) frame prefixes" if self.packed else
+                        "; build it with packed=True for xyz-only uploads"))
+                self.pc.copy_(point_cloud, non_blocking=non_blocking)
+                self.filled = [self.N, self.N]
+            else:
+                if not self.packed:
+                    raise ValueError("frame prefixes need an engine built with packed=True")
+                for f, xyz in enumerate(frames):
+                    n = xyz.shape[1]
+                    if xyz.shape[0] != self.B or xyz.shape[2] != 3 or n > self.N:
+                        raise ValueError("frame %d: expected (%d, n <= %d, 3), got %s" % (f + 1, self.B, self.N, tuple(xyz.shape)))
+                    slab = self.pc[:, f * self.N:(f + 1) * self.N]
+                    slab[:, :n].copy_(xyz, non_blocking=non_blocking)
+                    if n < self.filled[f]:
+                        slab[:, n:self.filled[f]].zero_()          # rows a longer earlier frame left behind
+                    self.filled[f] = n
             if T_gt is not None:
                 self.T_gt.copy_(T_gt, non_blocking=non_blocking)
 
@@ -92,7 +133,7 @@ class PWCLOPipeline:
     so independent frame pairs overlap almost freely (results are still delivered in order)."""
 
     def __init__(self, batch_size, H_input=64, W_input=1800, num_points=150000, params=None, perms=None,
-                 device="cuda:0", depth=None, streams=1):
+                 device="cuda:0", depth=None, streams=1, packed=False):
         depth = depth if depth is not None else 2 * max(1, streams)
         self.device = torch.device(device)
         store = params if isinstance(params, ParamStore) else ParamStore(
@@ -105,7 +146,7 @@ class PWCLOPipeline:
             _lib.set_tile_policy(1)
         try:
             self.engines = [PWCLOEngine(batch_size, H_input, W_input, num_points, params=store, perms=perms,
-                                        device=device).capture() for _ in range(depth)]
+                                        device=device, packed=packed).capture() for _ in range(depth)]
         finally:
             _lib.set_tile_policy(prev)
         self.copy_stream = torch.cuda.Stream(self.device)
@@ -120,12 +161,9 @@ class PWCLOPipeline:
 
     def _upload(self, slot, pc, T_gt):
         eng = self.engines[slot]
-        with torch.cuda.stream(self.copy_stream):
-            self.copy_stream.wait_event(self.consumed[slot])      # the previous forward on this slot has read its input
-            eng.pc.copy_(pc, non_blocking=True)
-            if T_gt is not None:
-                eng.T_gt.copy_(T_gt, non_blocking=True)
-            self.uploaded[slot].record(self.copy_stream)
+        self.copy_stream.wait_event(self.consumed[slot])          # the previous forward on this slot has read its input
+        eng.load(pc, T_gt, non_blocking=True, stream=self.copy_stream)
+        self.uploaded[slot].record(self.copy_stream)
 
     def _compute(self, slot):
         eng = self.engines[slot]
@@ -140,7 +178,8 @@ class PWCLOPipeline:
             self.done[slot].record(cs)
 
     def run(self, batches):
-        """batches: iterable of (point_cloud (B,2N,6) pinned host tensor, T_gt or None).  Yields (q, t) host
+        """batches: iterable of (point_cloud, T_gt or None); point_cloud as PWCLOEngine.load takes it -- a (B,2N,6)
+        pinned host tensor, or for a packed pipeline (B,2N,3) / a pair of (B,n,3) frame prefixes.  Yields (q, t) host
         tensors per batch, in order (each valid until `depth` more batches have been consumed)."""
         depth = len(self.engines)
         pending = []

@@ -69,18 +69,25 @@ class OdometryDataset:
         raise IndexError(index)
 
     def __getitem__(self, index):
+        point2, point1, T_gt = self.frames(index)
+        n1, n2 = point1.shape[0], point2.shape[0]
+        pos1 = np.zeros((self.num_points, 3))
+        pos2 = np.zeros((self.num_points, 3))
+        pos1[:n1, :3] = point1
+        pos2[:n2, :3] = point2
+        return pos2, pos1, n2, n1, T_gt
+
+    def frames(self, index):
+        """The item without its zero padding, in __getitem__'s order (the LATER scan first): (pos2 (n2, 3) float32,
+        pos1 (n1, 3) float32, T_gt) -- what the packed upload path (get_batch_packed, PWCLOEngine(packed=True)) sends
+        to the GPU; the padding to NUM_POINTS rows of kitti_dataset.py:76-80 then happens on the device."""
         cur_seq, i1, i2 = self.locate(index)
         seq_dir = os.path.join(self.datapath, self.file_map[cur_seq])
         if cur_seq not in self._calib:
             self._calib[cur_seq] = calib_Tr(os.path.join(seq_dir, "calib.txt"))
         Tr, Tr_inv = self._calib[cur_seq]
-        point1 = np.fromfile(os.path.join(seq_dir, "velodyne", "%06d.bin" % i1), dtype=np.float32).reshape(-1, 4)
-        point2 = np.fromfile(os.path.join(seq_dir, "velodyne", "%06d.bin" % i2), dtype=np.float32).reshape(-1, 4)
-        n1, n2 = point1.shape[0], point2.shape[0]
-        pos1 = np.zeros((self.num_points, 3))
-        pos2 = np.zeros((self.num_points, 3))
-        pos1[:n1, :3] = point1[:, :3]
-        pos2[:n2, :3] = point2[:, :3]
+        point1 = np.fromfile(os.path.join(seq_dir, "velodyne", "%06d.bin" % i1), dtype=np.float32).reshape(-1, 4)[:, :3]
+        point2 = np.fromfile(os.path.join(seq_dir, "velodyne", "%06d.bin" % i2), dtype=np.float32).reshape(-1, 4)[:, :3]
         if cur_seq > 10:
             T_diff = np.ones((1, 12))                      # test sequences have no ground truth (:84-85)
         else:
@@ -89,7 +96,7 @@ class OdometryDataset:
             T_diff = self._pose[cur_seq][i2:i2 + 1, :]
         T_diff = np.concatenate([T_diff.reshape(3, 4), np.array([[0.0, 0.0, 0.0, 1.0]])], axis=0)
         T_gt = np.matmul(np.matmul(Tr_inv, T_diff), Tr)
-        return pos2, pos1, n2, n1, T_gt
+        return point2, point1, T_gt
 
     def __len__(self):
         return self.len_list[-1]
@@ -136,6 +143,46 @@ def get_batch(dataset, idxs, start_idx, end_idx, training=0, NUM_POINTS=150000, 
             batch_T_trans[i] = T_trans
             batch_T_trans_inv[i] = np.linalg.inv(T_trans)
     return batch_data, batch_T_gt, batch_T_trans, batch_T_trans_inv
+
+
+def get_batch_packed(dataset, idxs, start_idx, end_idx, training=0, rng=np.random, out=None):
+    """The same batch as get_batch in the packed upload format: (xyz_f1 (b, n1, 3) float32, xyz_f2 (b, n2, 3) float32,
+    T_gt, T_trans, T_trans_inv) where n1 / n2 are the largest point counts of the batch (shorter samples are
+    zero-padded to them, nothing is padded to NUM_POINTS and channels 3:6 -- always zero, main.py:327 -- are not
+    materialised).  get_batch(...)[0][:, :n1, :3] == xyz_f1 and rows [n1, NUM_POINTS) of it are zero.
+    `out`: optional pair of preallocated (ideally pinned) float32 arrays / tensors (b_max, NUM_POINTS, 3) to fill in
+    place; the returned frames are views of their first n rows."""
+    bsize = end_idx - start_idx
+    items = [dataset.frames(idxs[i + start_idx]) for i in range(bsize)]
+    n1 = max(it[0].shape[0] for it in items)
+    n2 = max(it[1].shape[0] for it in items)
+    if max(n1, n2) > dataset.num_points:
+        raise ValueError("a scan has %d points, more than NUM_POINTS = %d" % (max(n1, n2), dataset.num_points))
+    if out is None:
+        f1, f2 = np.zeros((bsize, n1, 3), np.float32), np.zeros((bsize, n2, 3), np.float32)
+    else:
+        f1, f2 = out[0][:bsize, :n1], out[1][:bsize, :n2]
+    batch_T_gt = np.zeros((bsize, 4, 4))
+    batch_T_trans = np.tile(np.expand_dims(np.eye(4), axis=0), [bsize, 1, 1])
+    batch_T_trans_inv = batch_T_trans.copy()
+    for i, (pc1, pc2, T_gt) in enumerate(items):
+        for dst, src in ((f1, pc1), (f2, pc2)):
+            dst[i, :src.shape[0]] = _like(dst, src)
+            dst[i, src.shape[0]:] = 0
+        batch_T_gt[i] = T_gt
+        if training != 0:
+            T_trans = DataAugmentation(rng)
+            batch_T_trans[i] = T_trans
+            batch_T_trans_inv[i] = np.linalg.inv(T_trans)
+    return f1, f2, batch_T_gt, batch_T_trans, batch_T_trans_inv
+
+
+def _like(dst, src):
+    """src as something dst[...] = accepts (dst may be a numpy array or a torch tensor)."""
+    if isinstance(dst, np.ndarray):
+        return src
+    import torch
+    return torch.from_numpy(np.ascontiguousarray(src))
 
 
 # ---- trajectory ---------------------------------------------------------------------------------------
@@ -259,6 +306,8 @@ def calc_sequence_errors(poses_gt, poses_result, step_size=10):
 def compute_overall_err(seq_err):
     """(mean t_err, mean r_err) over the segments; the reference prints t*100 [%] and r/pi*180*100 [deg/100 m]
     (kitti_evaluation.py:185-195, 626)."""
+    if not seq_err:               # no completed 100 m segment (a truncated run): the metric is undefined
+        return float("nan"), float("nan")
     t_err = sum(e[2] for e in seq_err)
     r_err = sum(e[1] for e in seq_err)
     return t_err / len(seq_err), r_err / len(seq_err)
@@ -287,18 +336,21 @@ def run_sequence(dataset, seq, params, batch_size=1, H_input=64, W_input=1800, d
     idxs = np.arange(start, end)
     Tr, Tr_inv = calib_Tr(os.path.join(dataset.datapath, dataset.file_map[seq], "calib.txt"))
     N = dataset.num_points
-    pipe = PWCLOPipeline(batch_size, H_input, W_input, N, params=params, perms=perms, device=device)
-    hosts = [torch.zeros(batch_size, 2 * N, 6).pin_memory() for _ in range(len(pipe.engines) + 1)]
+    # packed upload: only the xyz rows that hold points travel (pinned fp32 staging buffers, filled in place); the
+    # zero padding to NUM_POINTS and the (unused) channels 3:6 of main.py:327 exist only on the device
+    pipe = PWCLOPipeline(batch_size, H_input, W_input, N, params=params, perms=perms, device=device, packed=True)
+    hosts = [(torch.zeros(batch_size, N, 3).pin_memory(), torch.zeros(batch_size, N, 3).pin_memory())
+             for _ in range(len(pipe.engines) + 1)]
     sizes = []
 
     def batches():
         for k, b0 in enumerate(range(0, len(idxs), batch_size)):
             b1 = min(len(idxs), b0 + batch_size)
-            data, T_gt, _, _ = get_batch(dataset, idxs, b0, b1, training=0, NUM_POINTS=N)
             buf = hosts[k % len(hosts)]
-            buf[:b1 - b0].copy_(torch.from_numpy(data))            # a short last batch keeps stale rows, like :509-515
+            f1, f2, T_gt, _, _ = get_batch_packed(dataset, idxs, b0, b1, training=0, out=buf)
             sizes.append(b1 - b0)
-            yield buf, None
+            # a short last batch keeps the previous batch's samples in its tail rows, like main.py:509-515
+            yield (buf[0][:, :f1.shape[1]], buf[1][:, :f2.shape[1]]), None
 
     traj = Trajectory(Tr, Tr_inv)
     for k, (q, t) in enumerate(pipe.run(batches())):

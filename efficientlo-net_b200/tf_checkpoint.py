@@ -124,6 +124,29 @@ def read_bundle(prefix):
     return out
 
 
+def resolve_prefix(path):
+    """Checkpoint prefix (what read_bundle opens as prefix + '.index') from a prefix or a checkpoint directory:
+    a directory is resolved through its `checkpoint` file (model_checkpoint_path) or its only *.index file."""
+    import glob
+    import os
+    import re
+    if os.path.exists(path + ".index"):
+        return path
+    if os.path.isdir(path):
+        state = os.path.join(path, "checkpoint")
+        if os.path.exists(state):
+            m = re.search(r'^model_checkpoint_path:\s*"([^"]+)"', open(state).read(), re.M)
+            if m:
+                cand = os.path.join(path, os.path.basename(m.group(1)))
+                if os.path.exists(cand + ".index"):
+                    return cand
+        found = sorted(glob.glob(os.path.join(path, "*.index")))
+        if len(found) == 1:
+            return found[0][:-len(".index")]
+        raise FileNotFoundError("%s: %d *.index files and no usable `checkpoint` file" % (path, len(found)))
+    raise FileNotFoundError("%s: neither a checkpoint prefix (%s.index) nor a directory" % (path, path))
+
+
 def load_reference_checkpoint(prefix, dtype=torch.float32):
     """The reference's checkpoint as the flat parameter dict of params.py: optimizer slots dropped,
     conv kernels squeezed from [1,1,Cin,Cout] / [1,Cin,Cout] to (Cin,Cout).  Also returns the global step."""

@@ -11,6 +11,13 @@ from oracle import graph_oracle as go
 
 pytestmark = pytest.mark.gpu
 RTOL, ATOL = 1e-4, 1e-5
+# Index work with a tolerance (row a10): a point whose azimuth / elevation sits on a bin edge to the last bit lands in
+# the adjacent cell when CUDA's atan2f / asinf and the host libm of the restatement round differently.  The counts
+# below are what the B200 run of this test measured (printed by the tests, recorded in DESIGN.md section 5); the
+# tests fail above them.
+PROJ_MOVED_MAX = 2       # measured (r2): 2, an adjacent pair [2,54,263]/[2,54,264]; of 4 x 64 x 1800 cells (input projection, two frames of two samples)
+CHAIN_ATOL = 5e-5        # intermediates of the full chain: 1e-4 relative + this (measured need: see the test's print)
+REPROJ_MOVED_MAX = 0     # measured (r2): 0 at every level; of 2 x h x w cells per refinement level
 H_IN, W_IN, NPTS = 64, 1800, 150000
 
 
@@ -67,7 +74,8 @@ def test_input_projection_and_preprocess(elo, world):
     # CUDA's atan2f / asinf and the host libm may round differently and the point moves to the ADJACENT cell.
     diff = (xyz.cpu() != want).any(-1)
     cells = diff.nonzero().tolist()
-    assert len(cells) <= 4, "%d cells differ: %s" % (len(cells), cells[:8])
+    print("input projection: %d of %d cells differ from the restatement: %s" % (len(cells), diff.numel(), cells))
+    assert len(cells) <= PROJ_MOVED_MAX, "%d cells differ: %s" % (len(cells), cells[:8])
     for b, h, w in cells:
         assert any(c[0] == b and abs(c[1] - h) + abs(c[2] - w) == 1 for c in cells), "isolated differing cell %s" % [b, h, w]
     assert bool((world["pc"][:, :NPTS, 0] == 0).logical_and(torch.signbit(world["pc"][:, :NPTS, 0])).any())
@@ -77,7 +85,9 @@ def test_input_projection_and_preprocess(elo, world):
     xyz_plain, again = elo.ProjectPC2SphericalRing(f1, None, H_IN, W_IN)
     want_plain, _ = go.ProjectPC2SphericalRing(world["pc"][:, :NPTS, 0:3], None, H_IN, W_IN)
     assert again is xyz_plain
-    assert int((xyz_plain.cpu() != want_plain).any(-1).sum()) <= 4
+    nplain = int((xyz_plain.cpu() != want_plain).any(-1).sum())
+    print("plain ProjectPC2SphericalRing: %d cells differ" % nplain)
+    assert nplain <= PROJ_MOVED_MAX
 
 
 @pytest.mark.parametrize("lvl", [2, 1, 0])
@@ -96,7 +106,8 @@ def test_warp_and_reprojection(elo, world, lvl):
     # the warp is written without FMA contraction in the reference's operation order: bit-exact
     assert torch.equal(warped.cpu(), keep["l%d_flow_warp" % lvl]), "warp differs"
     bad = (xyz_wp.cpu() != keep["l%d_xyz_warp_proj" % lvl]).any(-1)
-    assert int(bad.sum()) <= 2
+    print("re-projection l%d: %d of %d cells differ" % (lvl, int(bad.sum()), bad.numel()))
+    assert int(bad.sum()) <= REPROJ_MOVED_MAX
     ok = ~bad
     close(pts_wp.cpu()[ok], keep["l%d_points_warp_proj" % lvl][ok], "re-projected features l%d" % lvl)
 
@@ -235,11 +246,13 @@ def test_full_forward_matches_oracle(elo, world):
     for k in ("l0_points_f1", "l1_points_f2", "l2_points_f1", "l3_points_f2", "l2_points_f1_new",
               "l3_points_f1_cost_volume", "l3_q", "l3_t", "l2_cost_volume", "l2_predict", "l2_w", "l2_q", "l2_t",
               "l1_cost_volume", "l1_predict", "l1_q", "l1_t", "l0_cost_volume", "l0_predict", "l0_w", "l0_pooled"):
-        err = (keep[k].cpu().double() - world["keep"][k].double()).abs().max().item()
-        report.append("%s %.2e" % (k, err))
-        # intermediates of the full chain (each block is held to 1e-4 on its own in the block tests; errors of
-        # the upstream blocks compound here, hence the wider band)
-        close(keep[k], world["keep"][k], "intermediate " + k, rtol=1e-3, atol=2e-4)
+        g, w_ = keep[k].cpu().double(), world["keep"][k].double()
+        err = (g - w_).abs()
+        # absolute slack an element needs beyond 1e-4 relative: errors of the upstream blocks compound along the
+        # chain (each block is held to 1e-4 / 1e-5 on its own inputs in the block tests)
+        need = float((err - 1e-4 * w_.abs()).clamp_min(0).max())
+        report.append("%s max|err| %.2e  abs slack needed at rtol 1e-4: %.2e  (max|x| %.2f)" % (k, err.max().item(), need, w_.abs().max().item()))
+        close(keep[k], world["keep"][k], "intermediate " + k, rtol=1e-4, atol=CHAIN_ATOL)
     print("\n".join(report))
     for n, g, w in zip(names, out, world["out"]):
         close(g, w, "get_model output " + n, rtol=1e-4, atol=2e-5)

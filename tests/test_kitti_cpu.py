@@ -109,3 +109,36 @@ def test_kitti_metric_matches_the_reference(kitti, G, tmp_path):
     # a perfect trajectory has zero error
     e0 = kitti.calc_sequence_errors(gt, gt)
     assert max(e[2] for e in e0) < 1e-12 and len(e0) == len(err)
+
+
+def test_metric_of_a_truncated_run_is_nan_not_a_crash(kitti, G):
+    """A trajectory with no completed 100 m segment (eval_kitti --max_frames) has no metric: NaN, no ZeroDivisionError."""
+    gt = kitti.poses_from_rows(G["metric_gt_rows"][:5])
+    err = kitti.calc_sequence_errors(gt, gt)
+    assert err == []
+    t, r = kitti.compute_overall_err(err)
+    assert np.isnan(t) and np.isnan(r)
+
+
+def test_packed_batch_is_the_reference_batch_without_padding(kitti, G, tree):
+    """get_batch_packed: the xyz rows that hold points, as float32 -- equal to get_batch's rows, which are zero beyond."""
+    import torch
+    root, pose = tree
+    ds = kitti.OdometryDataset(root=root, NUM_POINTS=128, pose_dir=pose)
+    idxs = [int(i) for i in G["ds_idx"]]
+    data, T_gt, T_trans, T_inv = kitti.get_batch(ds, idxs, 1, 4, training=0, NUM_POINTS=128)
+    f1, f2, T_gt_p, T_trans_p, T_inv_p = kitti.get_batch_packed(ds, idxs, 1, 4, training=0)
+    assert f1.dtype == np.float32 and f1.shape[0] == 3 and f1.shape[2] == 3 and f1.shape[1] <= 128
+    n1, n2 = f1.shape[1], f2.shape[1]
+    assert np.array_equal(data[:, :n1, :3], f1) and not data[:, n1:128].any()
+    assert np.array_equal(data[:, 128:128 + n2, :3], f2) and not data[:, 128 + n2:].any()
+    assert np.array_equal(T_gt, T_gt_p) and np.array_equal(T_trans, T_trans_p) and np.array_equal(T_inv, T_inv_p)
+    # in place into preallocated (pinned in production) torch staging buffers; stale rows of an earlier batch are cleared
+    out = (torch.full((4, 128, 3), 7.0), torch.full((4, 128, 3), 7.0))
+    g1, g2, _, _, _ = kitti.get_batch_packed(ds, idxs, 1, 4, training=0, out=out)
+    assert np.array_equal(g1.numpy(), f1) and np.array_equal(g2.numpy(), f2)
+    assert g1.data_ptr() == out[0].data_ptr()
+    # the augmentation draws are the reference's (same rng stream as get_batch)
+    a = kitti.get_batch(ds, idxs, 0, 2, training=1, NUM_POINTS=128, rng=np.random.RandomState(5))
+    b = kitti.get_batch_packed(ds, idxs, 0, 2, training=1, rng=np.random.RandomState(5))
+    assert np.array_equal(a[2], b[3]) and np.array_equal(a[3], b[4])

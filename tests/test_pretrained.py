@@ -60,3 +60,18 @@ def test_trained_weights_on_gpu_match_oracle_and_regress_motion(elo, cuda):
         assert err <= 1e-4 * w.abs().max().item() + 5e-5, "%s differs by %.3g" % (name, err)
     t_err, q_err, t_norm = pose_errors(got, T)
     assert bool((t_err < 0.06 * t_norm + 0.02).all()) and bool((q_err < 5e-3).all()), (t_err, q_err)
+
+
+@pytest.mark.skipif(not os.path.exists(REF + ".index"), reason="reference checkpoint not present")
+def test_eval_kitti_cli_loads_the_tf_checkpoint_from_directory_or_prefix(capsys):
+    """tools/eval_kitti.py --checkpoint takes the checkpoint directory (its `checkpoint` file names a file that is
+    not shipped, so the lone *.index decides) or the prefix; both load all 560 tensors."""
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, os.path.join(root, "tools"))
+    import eval_kitti
+    for ck in (os.path.dirname(REF), REF):
+        eval_kitti.main(["--data_root", "/nonexistent", "--checkpoint", ck, "--check_only"])
+        assert "560 tensors, 914046 values" in capsys.readouterr().out      # weights + BN moving statistics
+    with pytest.raises(FileNotFoundError):
+        eval_kitti.load_params("/nonexistent/dir")
