@@ -17,7 +17,7 @@ from oracle import graph_oracle as go
 
 pytestmark = pytest.mark.gpu
 H_IN, W_IN, NPTS = 64, 1800, 150000
-MOVED_MAX = 18          # cells of 2 x 2 x 64 x 1800 that differ after a real augmentation: 18 measured on the B200 (r2)
+MOVED_MAX = 4           # cells of 2 x 2 x 64 x 1800 that differ after a real augmentation: 4 measured on the B200 (r2)
 
 
 def coord_tol(want):
