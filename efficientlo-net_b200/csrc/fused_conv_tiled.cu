@@ -37,6 +37,7 @@
 
 #include "../../include/elo_b200.h"
 #include "elo_common.cuh"
+#include "elo_count_rows.cuh"
 #include "elo_search.cuh"
 
 namespace elo {
@@ -70,6 +71,7 @@ struct TiledParams {
     int vec_ok;          // every output pointer is 16-byte aligned
     unsigned magic_kt;   // ceil(2^32 / kt), ceil(2^32 / K): exact quotients for the writer's ranges
     unsigned magic_k;
+    int dbg;             // timing aid (ELO_TILED_DBG): 1 = query warps skip the walk, 2 = store warp skips its rows
     int pitch;           // row pitch of the staged tile in cells (TQ + kW)
     float near_bound;    // sqrt(distance^2 / 12.5): coordinates within it are all mutually in range
     int walk[MAX_WALK];  // select-K: window cells centre-out, (dh << 16) | (dw & 0xffff)
@@ -91,14 +93,6 @@ __device__ __forceinline__ int wrap_once(int ww, int w2)
     return ww;
 }
 
-__device__ __forceinline__ unsigned udiv_magic(unsigned e, unsigned magic, unsigned d, unsigned& rem)
-{
-    unsigned q = __umulhi(e, magic);
-    rem = e - q * d;
-    if (rem >= d) { rem -= d; ++q; }      // magic = 2^32 - 1 stands in for d = 1
-    return q;
-}
-
 // One insertion into the ascending array a[0..KR): afterwards a holds the KR smallest of (a, x).
 // Branch-free and without a serial chain: a'[i] = min(a[i], max(a[i-1], x)).
 template <int KR>
@@ -113,10 +107,32 @@ __device__ __forceinline__ void chain_insert(unsigned (&a)[KR], unsigned x)
     }
 }
 
-template <bool SELECT, int KR, int TQ>
-__global__ void __launch_bounds__(TQ, (KR <= 17 ? 896 / TQ : 512 / TQ)) fused_conv_tiled_kernel(const __grid_constant__ TiledParams p)
+// Threads per CTA: TQ query threads; a select-K CTA has one more warp, the STORE WARP.  The counts of a select-K
+// do not depend on the selection (the reference's walk visits all kt cells: valid_idx counts the non-empty in-image
+// cells, valid_in_dis_idx those in range), and when every point of the neighbourhood is in range of every centre
+// both are a box sum over the staged emptiness flags.  The store warp computes them right after the staging and
+// streams out the CTA's 2 x TQ count rows (83 % of the op's bytes) WHILE the query warps walk their windows: the
+// store-bound and the issue-bound halves of the op overlap, and the stores sit in the queue of a warp that has
+// nothing else to do (stores issued early by the query threads themselves back-pressure their own shared-memory
+// loads: DESIGN.md section 4.1).
+template <bool SW, int TQ>
+constexpr int tiled_threads() { return TQ + (SW ? 32 : 0); }
+template <bool SELECT, int KR, int TQ, bool SW>
+constexpr int tiled_min_ctas()
 {
-    constexpr int TW = TQ / 32;   // warps per CTA
+    // one wave of CTAs on 148 SMs for 115 200 queries needs 5 x 160 query threads per SM; with the store warp that
+    // is 960 threads, i.e. 64 registers per thread instead of 72
+    if (!SW) return KR <= 17 ? 896 / TQ : 512 / TQ;
+    return KR <= 17 ? (TQ == 128 ? 6 : TQ == 160 ? 5 : 4) : 512 / tiled_threads<SW, TQ>();
+}
+
+template <bool SELECT, int KR, int TQ, bool SW>
+__global__ void __launch_bounds__((tiled_threads<SW, TQ>()), (tiled_min_ctas<SELECT, KR, TQ, SW>()))
+fused_conv_tiled_kernel(const __grid_constant__ TiledParams p)
+{
+    static_assert(SELECT || !SW, "only select-K has a store warp");
+    constexpr int TW = TQ / 32;   // query warps per CTA
+    constexpr int NT = tiled_threads<SW, TQ>();
     extern __shared__ __align__(16) unsigned char smem_raw[];
     pdl_trigger();
     pdl_wait();
@@ -138,13 +154,16 @@ __global__ void __launch_bounds__(TQ, (KR <= 17 ? 896 / TQ : 512 / TQ)) fused_co
     int* s_first = reinterpret_cast<int*>(take(TQ * 4));
     int* s_bcopy = reinterpret_cast<int*>(take(TQ * 4));                     // b << 1 | copy
     int* s_ties = reinterpret_cast<int*>(take(TQ * 4));
+    int* s_qpos = reinterpret_cast<int*>(take(TQ * 4));                      // tile cell of the window's corner, or -1
+    int* s_vsum = reinterpret_cast<int*>(take((size_t)(p.pitch + 1) * 4));   // store warp: prefix of the column sums
     int* s_misc = reinterpret_cast<int*>(take(64));                          // tie count, reference column, geometry
     unsigned char* tile = take((size_t)p.tile_bytes);                        // float4 per cell; replay scratch later
 
     // ---- this thread's query -----------------------------------------------------------------------
     const long long q0 = (long long)blockIdx.x * TQ;
     const long long q = q0 + tid;
-    const bool active = q < p.total;
+    const bool store_warp = SW && tid >= TQ;
+    const bool active = q < p.total && !store_warp;
     int b = 0, h = 0, w = 0;
     float xc = 0.f, yc = 0.f, zc = 0.f;
     bool cvalid = false;
@@ -228,86 +247,13 @@ __global__ void __launch_bounds__(TQ, (KR <= 17 ? 896 / TQ : 512 / TQ)) fused_co
     // ---- row writers.  Each warp writes the 32 rows of its own queries: no CTA-wide barrier between walk and
     //      write, so the warps of an SM drift apart and one warp's stores overlap another's arithmetic. -----------
     const int r_lo = warp * 32;                                           // first CTA-local row of this warp
-    const int nrows = (int)max(0ll, min(32ll, p.total - q0 - r_lo));
-    // valid_idx / valid_in_dis_idx rows are a run of ones followed by zeros.  Four rows are kt float4s,
-    // 16-byte aligned; a lane keeps the same float4 column f for every block of four rows, so which
-    // rows its four elements belong to (at most two when kt >= 4) and their positions are loop-invariant,
-    // and an element is saturate(count - position): one FADD.SAT on the FP32 pipe per element and row.
+    const int nrows = store_warp ? 0 : (int)max(0ll, min(32ll, p.total - q0 - r_lo));
+    // valid_idx / valid_in_dis_idx rows: elo_count_rows.cuh (skipped when the caller passed NULL for both, e.g. when
+    // the stand-alone count kernel of fused_conv_counts.cu writes them concurrently)
     float* const o_valid = (p.out_valid && nrows > 0) ? p.out_valid + (q0 + r_lo) * kt : nullptr;
     float* const o_vdis = (p.out_vdis && nrows > 0) ? p.out_vdis + (q0 + r_lo) * kt : nullptr;
-    const bool want_rows = o_valid != nullptr || o_vdis != nullptr;
-    const int nblk = (p.vec_ok && kt >= 4) ? nrows / 4 : 0;
-    const int nfi = (nblk > 0 && want_rows) ? (kt + 31) / 32 : 0;         // column chunks of 32 float4s
-    // column chunk fi: float4 column f = 32 fi + lane of every block of four rows.  Two warp-uniform
-    // shortcuts: no lane of the chunk straddles two rows (one term per element instead of two), and
-    // valid_in_dis_idx == valid_idx for all 32 queries (`same`: computed once, stored twice).
-    auto valid_rows_chunk = [&](int fi, bool same) {
-        const int f = 32 * fi + lane;
-        const bool on = f < kt;
-        unsigned pos0 = 0, pos3 = 0;
-        int r0 = 0, r3 = 0;
-        if (on) {
-            r0 = (int)udiv_magic(4u * f, p.magic_kt, (unsigned)kt, pos0);
-            r3 = (int)udiv_magic(4u * f + 3u, p.magic_kt, (unsigned)kt, pos3);
-        }
-        const bool straddle = __any_sync(FULL_MASK, on && r0 != r3);
-        if (!on) return;
-        // element i sits in row r0 at pos0 + i while that is < kt, else in row r3 at pos0 + i - kt
-        float pa[4], pb[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const bool lo = (int)pos0 + i < kt;
-            pa[i] = lo ? (float)((int)pos0 + i) : 1e9f;
-            pb[i] = lo ? 1e9f : (float)((int)pos0 + i - kt);
-        }
-        float4* ov = o_valid ? reinterpret_cast<float4*>(o_valid) + f : nullptr;
-        float4* od = o_vdis ? reinterpret_cast<float4*>(o_vdis) + f : nullptr;
-        const float* nva = s_nv + r_lo + r0; const float* nvb = s_nv + r_lo + r3;
-        const float* nsa = s_ns + r_lo + r0; const float* nsb = s_ns + r_lo + r3;
-        auto body = [&](auto STR, auto SAME) {
-            constexpr bool two = decltype(STR)::value, one_array = decltype(SAME)::value;
-#pragma unroll 4
-            for (int blk = 0; blk < nblk; ++blk) {
-                float a4[4], d4[4];
-                const float va = nva[4 * blk];
-#pragma unroll
-                for (int i = 0; i < 4; ++i) a4[i] = __saturatef(va - pa[i]);
-                if constexpr (two) {
-                    const float vb = nvb[4 * blk];
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) a4[i] += __saturatef(vb - pb[i]);
-                }
-                if constexpr (one_array) {
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) d4[i] = a4[i];
-                } else {
-                    const float da = nsa[4 * blk];
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) d4[i] = __saturatef(da - pa[i]);
-                    if constexpr (two) {
-                        const float db = nsb[4 * blk];
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) d4[i] += __saturatef(db - pb[i]);
-                    }
-                }
-                if (ov) __stcs(ov + (size_t)blk * kt, make_float4(a4[0], a4[1], a4[2], a4[3]));
-                if (od) __stcs(od + (size_t)blk * kt, make_float4(d4[0], d4[1], d4[2], d4[3]));
-            }
-        };
-        if (straddle) { if (same) body(std::true_type{}, std::true_type{}); else body(std::true_type{}, std::false_type{}); }
-        else          { if (same) body(std::false_type{}, std::true_type{}); else body(std::false_type{}, std::false_type{}); }
-    };
-    // rows that do not fill a block of four (or unaligned outputs): element by element
-    auto valid_rows_tail = [&]() {
-        if (!want_rows) return;
-        const unsigned nel = (unsigned)nrows * kt;
-        for (unsigned e = (unsigned)nblk * 4u * kt + lane; e < nel; e += 32) {
-            unsigned pos;
-            const unsigned r = r_lo + udiv_magic(e, p.magic_kt, (unsigned)kt, pos);
-            if (o_valid) o_valid[e] = (float)pos < s_nv[r] ? 1.0f : 0.0f;
-            if (o_vdis) o_vdis[e] = (float)pos < s_ns[r] ? 1.0f : 0.0f;
-        }
-    };
+    const bool count_rows = p.out_valid != nullptr || p.out_vdis != nullptr;      // CTA-uniform
+    bool early_rows = false;            // CTA-uniform: the store warp writes the count rows while the others walk
 
     if (tg.staged >= 0) {
         // ---- stage the tile: (x, y, z, 1 if the pixel is empty) ---------------------------------------------
@@ -323,7 +269,7 @@ __global__ void __launch_bounds__(TQ, (KR <= 17 ? 896 / TQ : 512 / TQ)) fused_co
             // a column of the tile per thread; its rows in groups of SR whose loads are all issued before any of
             // them is used (a plain row loop would pay one L2 round trip per row)
             constexpr int SR = 8;
-            for (int c = tid; c < tg.tw; c += TQ) {
+            for (int c = tid; c < tg.tw; c += NT) {
                 const int gc = (c0 + c) % g.w2;
                 for (int r0 = 0; r0 < tg.th; r0 += SR) {
                     float x[SR], y[SR], z[SR];
@@ -347,8 +293,10 @@ __global__ void __launch_bounds__(TQ, (KR <= 17 ? 896 / TQ : 512 / TQ)) fused_co
             }
         }
         if (far) s_misc[2] = 1;          // some coordinate of the neighbourhood is large, infinite or NaN
+        if (SELECT && !store_warp)       // where this query's window starts in the tile (for the store warp)
+            s_qpos[tid] = (staged && cvalid) ? (((ch - tg.hmin) << 16) | (rel - tg.rmin)) : -1;
         // ---- walk tables ----------------------------------------------------------------------------------
-        for (int j = tid; j < kt; j += TQ) {
+        for (int j = tid; j < kt; j += NT) {
             int pk, to;
             if (SELECT) {
                 pk = p.walk[j]; to = p.walk_to[j];
@@ -362,6 +310,49 @@ __global__ void __launch_bounds__(TQ, (KR <= 17 ? 896 / TQ : 512 / TQ)) fused_co
             walk_to[j] = to;
         }
         __syncthreads();
+        const bool all_near = SELECT && staged && s_misc[2] == 0;
+        early_rows = SW && all_near && count_rows;
+        if (store_warp) {
+            if (early_rows) {
+                // ---- store warp: counts of all TQ queries from the staged flags, then their 2 x TQ rows --------------
+                const float4* t4 = reinterpret_cast<const float4*>(tile);
+                for (int i = lane; i < TQ; i += 32) { s_nv[i] = 0.f; s_ns[i] = 0.f; }
+                // one pass per window-row offset that occurs in the CTA (1 or 2 for raster-order queries): column sums
+                // over the window's kH rows, exclusive prefix along the columns, then two look-ups per query
+                for (int dr = 0; dr + g.kH <= tg.th; ++dr) {
+                    int run = 0;
+                    for (int cb = 0; cb < tg.tw; cb += 32) {
+                        const int c = cb + lane;
+                        int sc = 0;
+                        if (c < tg.tw)
+                            for (int r = 0; r < g.kH; ++r) sc += (int)t4[(dr + r) * pitch + c].w;
+#pragma unroll
+                        for (int o = 1; o < 32; o <<= 1) {
+                            const int nb = __shfl_up_sync(FULL_MASK, sc, o);
+                            if (lane >= o) sc += nb;
+                        }
+                        if (c < tg.tw) s_vsum[c + 1] = run + sc;
+                        run += __shfl_sync(FULL_MASK, sc, 31);
+                    }
+                    if (lane == 0) s_vsum[0] = 0;
+                    __syncwarp();
+                    for (int i = lane; i < TQ; i += 32) {
+                        const int qp = s_qpos[i];
+                        if (qp >= 0 && (qp >> 16) == dr) {
+                            const int c0 = qp & 0xffff;
+                            const float n = (float)(kt - (s_vsum[c0 + g.kW] - s_vsum[c0]));
+                            s_nv[i] = n; s_ns[i] = n;
+                        }
+                    }
+                    __syncwarp();
+                }
+                // all rows of the CTA in one go: the writer's per-column set-up is paid once per 32 float4 columns
+                const int nr = (int)max(0ll, min((long long)TQ, p.total - q0));
+                if (!(p.dbg & 2))
+                    write_count_rows(p.out_valid ? p.out_valid + q0 * kt : nullptr, p.out_vdis ? p.out_vdis + q0 * kt : nullptr,
+                                     nr, kt, p.vec_ok != 0, p.magic_kt, s_nv, s_ns, lane);
+            }
+        } else {
 
         // ---- the walk -----------------------------------------------------------------------------------
         const float* g2 = p.xyz2 + (size_t)b * g.h2 * g.w2 * 3;
@@ -376,9 +367,11 @@ __global__ void __launch_bounds__(TQ, (KR <= 17 ? 896 / TQ : 512 / TQ)) fused_co
 
         // ST = std::true_type: the window cells come from the staged tile; false_type: straight from the grid
         // NR = true_type (select-K on a staged tile only): every point is within range of every centre
-        auto walk = [&](auto ST, auto NR) {
+        // CN = true_type: the counts of valid / in-range cells are wanted (count rows are written by this kernel)
+        auto walk = [&](auto ST, auto NR, auto CN) {
             constexpr bool STG = decltype(ST)::value;
             constexpr bool NEAR = decltype(NR)::value;
+            constexpr bool CNT = decltype(CN)::value;
             float ninv = 0.f;             // staged walk: empty cells, counted on the FP32 pipe
             int nrej = 0;                 // ... and cells that are empty or out of range
             // direct path: cell j of the walk -> accepted?, distance; counts the valid cells
@@ -444,7 +437,7 @@ __global__ void __launch_bounds__(TQ, (KR <= 17 ? 896 / TQ : 512 / TQ)) fused_co
                 };
                 // NEAR: an empty pixel gets a key above every threshold, so the key test is the whole filter
                 auto eval_near = [&](const float4& c, float& d) {
-                    ninv += c.w;
+                    if constexpr (CNT) ninv += c.w;
                     d = fmaxf(sq3(__fsub_rn(xs, c.x), __fsub_rn(ys, c.y), __fsub_rn(zs, c.z)), 1e-10f);
                     return __fmaf_rn(c.w, 3e38f, d);
                 };
@@ -493,7 +486,14 @@ __global__ void __launch_bounds__(TQ, (KR <= 17 ? 896 / TQ : 512 / TQ)) fused_co
                     qp = qbase;
                     thr = a[KR - 1] | jmask;
                 }
-                if constexpr (NEAR) { nvalid = cvalid ? kt - (int)ninv : 0; nsel = nvalid; }
+                if constexpr (NEAR && CNT) { nvalid = cvalid ? kt - (int)ninv : 0; nsel = nvalid; }
+                if constexpr (NEAR && !CNT) {
+                    // no count rows to write: all that is needed is how many keys are real, min(in-range cells, KR)
+                    int nk = 0;
+#pragma unroll
+                    for (int i = 0; i < KR; ++i) nk += a[i] < KEY_NONE ? 1 : 0;
+                    nsel = nk; nvalid = nk;
+                }
                 if constexpr (STG && !NEAR) { nsel = kt - nrej; nvalid = kt - (int)ninv; }
                 if (!cvalid) { nsel = 0; nvalid = 0; }
                 // Near-ties: adjacent keys whose distance bits agree.  An isolated pair inside the K nearest is
@@ -502,6 +502,13 @@ __global__ void __launch_bounds__(TQ, (KR <= 17 ? 896 / TQ : 512 / TQ)) fused_co
                 // exact replay.
                 const int nw = min(nsel, K);
                 bool prev_eq = false;
+                // cheap screen first: the fix-up below is long straight-line code that most warps never need (two
+                // of a query's K nearest agree in the distance bits of the key in ~1 % of the queries)
+                bool any_eq = false;
+#pragma unroll
+                for (int i = 0; i + 1 < KR; ++i)
+                    any_eq = any_eq || (i < K && i + 1 < nsel && ((a[i] ^ a[i + 1]) & nmask) == 0u);
+                if (any_eq)
 #pragma unroll
                 for (int i = 0; i + 1 < KR; ++i) {
                     const bool eq = i < K && i + 1 < nsel && ((a[i] ^ a[i + 1]) & nmask) == 0u;
@@ -556,16 +563,20 @@ __global__ void __launch_bounds__(TQ, (KR <= 17 ? 896 / TQ : 512 / TQ)) fused_co
                 s_first[tid] = first;
             }
         };
-        const bool all_near = SELECT && staged && s_misc[2] == 0;
-        if (all_near) walk(std::true_type{}, std::true_type{});
-        else if (staged) walk(std::true_type{}, std::false_type{});
-        else walk(std::false_type{}, std::false_type{});
-        s_nv[tid] = (float)nvalid;
-        s_ns[tid] = (float)nsel;
+        // all_near with a store warp: the counts are not the walk's business -- the store warp has them
+        if (p.dbg & 1) { s_nwr[tid] = 0; s_first[tid] = 0; }
+        else if (all_near) {
+            if (SW || !count_rows) walk(std::true_type{}, std::true_type{}, std::false_type{});
+            else walk(std::true_type{}, std::true_type{}, std::true_type{});
+        }
+        else if (staged) walk(std::true_type{}, std::false_type{}, std::true_type{});
+        else walk(std::false_type{}, std::false_type{}, std::true_type{});
+        if (!early_rows) { s_nv[tid] = (float)nvalid; s_ns[tid] = (float)nsel; }
         // select-K duplicates entry 0 even when nothing was in range (mask 1, index (b,0,0)); random-K only
         // once a first neighbour was accepted (reference select :180-192, random :126-138)
         s_bcopy[tid] = (b << 1) | ((cvalid && g.flag_copy == 1 && (SELECT || nsel > 0)) ? 1 : 0);
-    } else {
+        }   // query warps
+    } else if (!store_warp) {
         s_nv[tid] = 0.f; s_ns[tid] = 0.f; s_nwr[tid] = 0; s_first[tid] = 0; s_bcopy[tid] = b << 1;
     }
     __syncwarp();
@@ -614,11 +625,8 @@ __global__ void __launch_bounds__(TQ, (KR <= 17 ? 896 / TQ : 512 / TQ)) fused_co
             o_mask[sl] = vm;
         }
     }
-    {
-        const bool same = __all_sync(FULL_MASK, s_nv[tid] == s_ns[tid]);
-        for (int fi = 0; fi < nfi; ++fi) valid_rows_chunk(fi, same);
-        valid_rows_tail();
-    }
+    if (!early_rows && !store_warp)
+        write_count_rows(o_valid, o_vdis, nrows, kt, p.vec_ok != 0, p.magic_kt, s_nv + r_lo, s_ns + r_lo, lane);
 
     // ---- exact replay of the tied queries (warp-cooperative, reference scan order), then their rows again ---------
     if (SELECT) {
@@ -628,9 +636,9 @@ __global__ void __launch_bounds__(TQ, (KR <= 17 ? 896 / TQ : 512 / TQ)) fused_co
             int2* off_scan = reinterpret_cast<int2*>(tile);
             float* dist = reinterpret_cast<float*>(tile + (size_t)kt * 8) + (size_t)warp * kt;
             int* hwv = reinterpret_cast<int*>(tile + (size_t)kt * 8 + (size_t)TW * kt * 4) + (size_t)warp * kt;
-            build_offsets(off_scan, p.random_hw, kt, g.kH, g.kW, TQ);
+            build_offsets(off_scan, p.random_hw, kt, g.kH, g.kW, NT);
             __syncthreads();
-            for (int t = warp; t < nties; t += TW) {
+            for (int t = warp; t < nties && !store_warp; t += TW) {
                 const int qt = s_ties[t];
                 const long long gq = q0 + qt;
                 const int bq = (int)(gq / p.N);
@@ -678,25 +686,30 @@ static unsigned magic_of(unsigned d)
     return (unsigned)(((1ull << 32) + d - 1) / d);
 }
 
-template <bool SELECT, int KR, int TQ>
+template <bool SELECT, int KR, int TQ, bool SW>
 static cudaError_t launch_tiled_kr(const TiledParams& p, size_t smem, cudaStream_t stream)
 {
-    auto kern = fused_conv_tiled_kernel<SELECT, KR, TQ>;
+    auto kern = fused_conv_tiled_kernel<SELECT, KR, TQ, SW>;
     if (smem > 48 * 1024) {
         cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (err != cudaSuccess) return err;
     }
     const long long ctas = (p.total + TQ - 1) / TQ;
-    return launch(kern, dim3((unsigned)ctas), dim3(TQ), smem, stream, p);
+    return launch(kern, dim3((unsigned)ctas), dim3(tiled_threads<SW, TQ>()), smem, stream, p);
 }
 
 template <int TQ>
-static cudaError_t launch_tiled_tq(bool select, const TiledParams& p, size_t smem, cudaStream_t stream)
+static cudaError_t launch_tiled_tq(bool select, bool sw, const TiledParams& p, size_t smem, cudaStream_t stream)
 {
-    if (!select) return launch_tiled_kr<false, 1, TQ>(p, smem, stream);
-    if (p.g.K <= 6) return launch_tiled_kr<true, 7, TQ>(p, smem, stream);
-    if (p.g.K <= 16) return launch_tiled_kr<true, 17, TQ>(p, smem, stream);
-    return launch_tiled_kr<true, 33, TQ>(p, smem, stream);
+    if (!select) return launch_tiled_kr<false, 1, TQ, false>(p, smem, stream);
+    if (sw) {
+        if (p.g.K <= 6) return launch_tiled_kr<true, 7, TQ, true>(p, smem, stream);
+        if (p.g.K <= 16) return launch_tiled_kr<true, 17, TQ, true>(p, smem, stream);
+        return launch_tiled_kr<true, 33, TQ, true>(p, smem, stream);
+    }
+    if (p.g.K <= 6) return launch_tiled_kr<true, 7, TQ, false>(p, smem, stream);
+    if (p.g.K <= 16) return launch_tiled_kr<true, 17, TQ, false>(p, smem, stream);
+    return launch_tiled_kr<true, 33, TQ, false>(p, smem, stream);
 }
 
 static size_t tiled_smem(const Window& g, bool select, int tq, int* tile_cap, int* tile_bytes)
@@ -707,7 +720,8 @@ static size_t tiled_smem(const Window& g, bool select, int tq, int* tile_cap, in
     size_t tb = (size_t)*tile_cap * 16;
     if (select) tb = std::max(tb, (size_t)g.kt * 8 + 2 * (size_t)(tq / 32) * g.kt * 4);   // replay scratch
     *tile_bytes = (int)up(tb);
-    return 2 * up((size_t)g.kt * 4) + up((size_t)std::max(g.K, QG) * tq * 4) + 6 * up((size_t)tq * 4) + up(64) + (size_t)*tile_bytes;
+    return 2 * up((size_t)g.kt * 4) + up((size_t)std::max(g.K, QG) * tq * 4) + 7 * up((size_t)tq * 4) +
+           up((size_t)(tq + g.kW + 1) * 4) + up(64) + (size_t)*tile_bytes;
 }
 
 // Everything of TiledParams that follows from the window: key layout, writer constants, the centre-out walk.
@@ -720,6 +734,7 @@ static void tiled_prepare(TiledParams& p, bool select)
     p.vec_ok = aligned(p.out_idx) && aligned(p.out_valid) && aligned(p.out_vdis) && aligned(p.out_mask) ? 1 : 0;
     p.magic_kt = magic_of((unsigned)g.kt);
     p.magic_k = magic_of((unsigned)g.K);
+    p.dbg = getenv("ELO_TILED_DBG") ? atoi(getenv("ELO_TILED_DBG")) : 0;
     if (select) {
         // centre-out walk: nearest pixels first, rows weighted 2x (a LiDAR's rows are ~2x further apart than
         // its columns), so the K-th key tightens early and few later cells pass the filter
@@ -738,7 +753,7 @@ static void tiled_prepare(TiledParams& p, bool select)
 }
 
 // The part that depends on the CTA size, then the launch.
-static cudaError_t tiled_launch(TiledParams& p, bool select, int tq, cudaStream_t stream)
+static cudaError_t tiled_launch(TiledParams& p, bool select, int tq, cudaStream_t stream, bool sw = false)
 {
     const Window& g = p.g;
     const size_t smem = tiled_smem(g, select, tq, &p.tile_cap, &p.tile_bytes);
@@ -751,9 +766,9 @@ static cudaError_t tiled_launch(TiledParams& p, bool select, int tq, cudaStream_
             p.walk_to[j] = ((dh + hh2) * p.pitch + (dw + hw2)) * 16;
         }
     }
-    if (tq == 128) return launch_tiled_tq<128>(select, p, smem, stream);
-    if (tq == 160) return launch_tiled_tq<160>(select, p, smem, stream);
-    return launch_tiled_tq<192>(select, p, smem, stream);
+    if (tq == 128) return launch_tiled_tq<128>(select, sw, p, smem, stream);
+    if (tq == 160) return launch_tiled_tq<160>(select, sw, p, smem, stream);
+    return launch_tiled_tq<192>(select, sw, p, smem, stream);
 }
 
 // Returns 1 when the tiled kernel took the call (status in *rc), 0 when the caller should use the
@@ -779,7 +794,18 @@ int launch_index_tiled(bool select, int B, int H, int W, int N, const Window& g,
     tiled_prepare(p, select);
 
     // CTA size: the candidate whose CTAs all fit on the chip at once and load the SMs most evenly
-    const int regs_cta_limit = (select && g.K > 16) ? 512 : 896;     // threads per SM the register budget allows
+    // CTAs per SM the register budget allows (tiled_min_ctas of the kernel template)
+    // A store warp (one more warp per CTA that writes the count rows while the query warps walk) pays for itself
+    // where the walk is long: measured on configs[0]'s frame, 11x41: 171.6 -> 148.7 us; 7x25: 68.3 -> 69.6 us
+    // (the query warps drop from 72 to 64 registers, and stores in flight slow the walk's shared-memory loads even
+    // from another warp); 5x15: 45.3 -> 48.0 us.  ELO_STORE_WARP_KT moves the switch-over.
+    static const int sw_min_kt = getenv("ELO_STORE_WARP_KT") ? atoi(getenv("ELO_STORE_WARP_KT")) : 256;
+    const bool sw = select && (out_valid != nullptr || out_vdis != nullptr) && g.kt >= sw_min_kt;
+    auto reg_ctas = [&](int tq) {
+        if (!sw) return (select && g.K > 16 ? 512 : 896) / tq;
+        if (g.K > 16) return 512 / (tq + 32);
+        return tq == 128 ? 6 : tq == 160 ? 5 : 4;
+    };
     int best_tq = 0;
     double best_cost = 0.0;
     for (int tq : {128, 160, 192}) {
@@ -787,7 +813,7 @@ int launch_index_tiled(bool select, int B, int H, int W, int N, const Window& g,
         const size_t smem = tiled_smem(g, select, tq, &cap, &tb);
         if (smem > 100 * 1024) continue;
         const long long ctas = (total + tq - 1) / tq;
-        const long long per_sm = std::min<long long>((long long)((dev.max_smem_optin + 1024) / (smem + 1024)), regs_cta_limit / tq);
+        const long long per_sm = std::min<long long>((long long)((dev.max_smem_optin + 1024) / (smem + 1024)), (long long)reg_ctas(tq));
         if (per_sm < 1) continue;
         const long long rounds = (ctas + dev.sm_count - 1) / dev.sm_count;     // CTAs the busiest SM runs
         double cost = (double)rounds * tq;                                      // queries on the busiest SM
@@ -795,7 +821,7 @@ int launch_index_tiled(bool select, int B, int H, int W, int N, const Window& g,
         if (best_tq == 0 || cost < best_cost) { best_tq = tq; best_cost = cost; }
     }
     if (best_tq == 0) return 0;
-    const cudaError_t err = tiled_launch(p, select, best_tq, stream);
+    const cudaError_t err = tiled_launch(p, select, best_tq, stream, sw);
     *rc = err == cudaSuccess ? ELO_OK : set_cuda_error(err, select ? "fused_conv_select_k (tiled) launch"
                                                                   : "fused_conv_random_k (tiled) launch");
     return 1;
