@@ -313,7 +313,138 @@ def index_op_roofline(elo, dev, peaks, iters=20, with_reference=False):
 
 
 def run_rowband(args, rank, world, dev, dist):
-    raise SystemExit("--partition rowband: not wired up yet")
+    """--partition rowband: ALL ranks work on ONE frame pair at a time (BASELINE.json north_star: row bands of the
+    projected image, one exchange per banded pyramid level over NCCL / NVLink).  A step = one complete forward of one
+    pair on the whole group, steps back to back (this is a latency mode: value = pairs/s of the group, strong scaling).
+    Rank 0 also times the same pairs on its own GPU alone and compares the poses."""
+    import torch
+    import elo_b200 as elo
+    B = 1
+    elo._lib.set_tile_policy(0)
+    store = elo.ParamStore(elo.params.init_params(0), dev)
+    perms = elo.params.make_perms(0)
+    band = elo.RowBand(rank, world)
+    pool = args.pool if args.pool > 0 else 8
+    host = [elo.synth.synth_batch(B, H_IN, W_IN, NPTS, seed0=i) for i in range(pool)]      # the same pairs on every rank
+
+    def make(band_):
+        engines = []
+        for i in range(pool):
+            eng = elo.PWCLOEngine(B, H_IN, W_IN, NPTS, params=store, perms=perms, device=dev, band=band_)
+            eng.load(*host[i], non_blocking=False)
+            n0 = elo._lib.launch_count()
+            eng.capture()
+            per = (elo._lib.launch_count() - n0) // 3
+            engines.append(eng)
+        st = engines[0].stream
+        for e in engines:
+            e.stream = st
+        return engines, st, per
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if dist is not None:
+            dist.barrier()
+            torch.cuda.synchronize(dev)
+
+    def timed(engines, st, count, together):
+        if together:
+            barrier()
+        else:
+            torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(st):
+            e0.record(st)
+            for i in range(count):
+                engines[i % pool].run()
+            e1.record(st)
+        if together:
+            barrier()
+        else:
+            torch.cuda.synchronize(dev)
+        return e0.elapsed_time(e1)
+
+    def max_over_ranks(v):
+        if dist is None:
+            return v
+        t = torch.tensor([v], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    engines, st, per_forward = make(band if world > 1 else None)
+    timed(engines, st, args.warmup, True)
+    sampler = ClockSampler(dev.index or 0)
+    sampler.start()
+    R = args.rounds if args.rounds > 0 else 9
+    rounds = [max_over_ranks(timed(engines, st, args.steps, True)) for _ in range(R)]
+    clocks = sampler.summary()
+    ms = median(rounds)
+    exchanges = band.exchanges // max(1, 3 * pool) if world > 1 else 0      # counted while tracing: 3 forwards per engine
+    outs_banded = [tuple(o.clone() for o in engines[i].outputs[:8]) for i in range(min(pool, 2))]
+
+    # e2e: every step uploads the pair (packed xyz prefixes, pinned) on every rank and reads (q, t) back, synchronously
+    n_real = H_IN * W_IN
+    pinned = [((pc[:, :n_real, :3].contiguous().pin_memory(), pc[:, NPTS:NPTS + n_real, :3].contiguous().pin_memory()),
+               T.pin_memory()) for pc, T in host]
+    peng = elo.PWCLOEngine(B, H_IN, W_IN, NPTS, params=store, perms=perms, device=dev, band=band if world > 1 else None,
+                           packed=True)
+    peng.load(*pinned[0], non_blocking=False)
+    peng.capture()
+    for i in range(3):
+        peng.infer(*pinned[i % pool])
+
+    def e2e_round():
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(args.steps):
+            peng.infer(*pinned[i % pool])
+        dt = 1e3 * (time.perf_counter() - t0)
+        return max_over_ranks(dt)
+
+    e2e_ms = median([e2e_round() for _ in range(3)])
+
+    # the same pairs on ONE GPU (rank 0 alone, the others wait): latency to beat, and the poses to reproduce
+    single_ms, pose_diff = None, None
+    if world > 1:
+        barrier()
+        if rank == 0:
+            ref, rst, _ = make(None)
+            timed(ref, rst, args.warmup, False)
+            single_ms = median([timed(ref, rst, args.steps, False) for _ in range(R)]) / args.steps
+            pose_diff = 0.0
+            for i, got in enumerate(outs_banded):
+                for g, w_ in zip(got, ref[i].outputs[:8]):
+                    pose_diff = max(pose_diff, float((g - w_).abs().max()))
+        barrier()
+    if rank == 0:
+        oh, _ = elo.pwclo_model.pyramid_shapes(H_IN, W_IN)
+        banded = ["layer0"] + ["l%d" % lvl for lvl in (0, 1, 2) if elo.RowBand(0, world).rows(oh[lvl + 2]) is not None] \
+            if world > 1 else []
+        line = {"metric": METRIC, "value": args.steps / (ms * 1e-3), "unit": "frame-pairs/s", "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+                "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": workload(B), "batch_per_gpu": B,
+                           "parallelism": "row bands of ONE frame pair over %d GPU(s): %s banded, one NCCL all-gather per "
+                                          "banded block chain (%d per forward), the other levels computed by every rank"
+                                          % (world, ", ".join(banded) or "nothing", exchanges),
+                           "mode": "latency: forwards of single pairs back to back on the whole group",
+                           "l2": "inputs rotate over %d distinct pairs" % pool,
+                           "graph": "whole forward incl. the NCCL exchanges captured as one CUDA graph per rank",
+                           "rounds": {"R": R, "value_round_ms": [round(x, 4) for x in sorted(rounds)]},
+                           "single_gpu_ms_per_forward": single_ms, "banded_ms_per_forward": ms / args.steps,
+                           "pose_max_abs_diff_vs_single_gpu": pose_diff},
+                "clocks": clocks,
+                "e2e": {"value": args.steps / (e2e_ms * 1e-3), "unit": "frame-pairs/s",
+                        "h2d_bytes_per_step": 2 * B * n_real * 3 * 4 + B * 64, "d2h_bytes_per_step": B * 7 * 4,
+                        "ms_per_step": e2e_ms / args.steps,
+                        "api": "PWCLOEngine(band=RowBand, packed=True).infer on every rank: upload of the pair's xyz rows "
+                               "from pinned host memory, banded forward, (q, t) read back, synchronous per step"},
+                "gpu_launches": per_forward * args.steps, "launches_per_step": per_forward,
+                "roofline": None, "cpu_baseline": None,
+                "mlp_engine": "tcgen05 tf32x3" if elo._lib.mlp_engine() == 1 else "fp32 FFMA"}
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
 
 
 def run_ours(args, rank, world, local_rank):

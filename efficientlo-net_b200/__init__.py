@@ -9,7 +9,7 @@ from .fused_conv import fused_conv_indices, fused_conv_random_k, fused_conv_sele
 from .model_util import (ProjectPC2SphericalRing, PreProcess, get_selected_idx, inv_q, mul_point_q,  # noqa: F401
                          mul_q_point, softmax_valid)
 from .pointnet_util import cost_volume, down_conv, flow_predictor, get_hw_idx, up_conv  # noqa: F401
-from .pwclo_model import get_loss, get_model, placeholder_inputs  # noqa: F401
+from .pwclo_model import RowBand, get_loss, get_model, placeholder_inputs  # noqa: F401
 from .store import ParamStore, use_store, variable_scope  # noqa: F401
 
 __version__ = "0.1.0"

@@ -31,12 +31,14 @@ class GroupMlpDesc(ctypes.Structure):
     _fields_ = [("batch_size", _c_int), ("queries", Queries), ("nsets", _c_int), ("set_batch_offset", _c_int * 2),
                 ("window", Window * 2), ("feat_channels", _c_int), ("num_layers", _c_int), ("cout", _c_int * 3),
                 ("xyz1", _c_void_p), ("xyz2", _c_void_p), ("feat2", _c_void_p * 2), ("weights", _c_void_p * 2),
-                ("out", _c_void_p * 2), ("dbg_nbr", _c_void_p * 2), ("nbr", _c_void_p * 2)]
+                ("out", _c_void_p * 2), ("dbg_nbr", _c_void_p * 2), ("nbr", _c_void_p * 2),
+                ("query_begin", _c_ll), ("query_end", _c_ll)]
 
 
 class SearchDesc(ctypes.Structure):
     _fields_ = [("select", _c_int), ("batch_size", _c_int), ("queries", Queries), ("window", Window),
-                ("xyz1", _c_void_p), ("xyz2", _c_void_p), ("out_nbr", _c_void_p)]
+                ("xyz1", _c_void_p), ("xyz2", _c_void_p), ("out_nbr", _c_void_p),
+                ("query_begin", _c_ll), ("query_end", _c_ll)]
 
 
 class CostVolumeDesc(ctypes.Structure):
@@ -44,7 +46,8 @@ class CostVolumeDesc(ctypes.Structure):
                 ("window_q", Window), ("window_p", Window),
                 ("xyz1", _c_void_p), ("xyz2", _c_void_p), ("f1", _c_void_p), ("f2", _c_void_p),
                 ("weights_1", _c_void_p), ("weights_2", _c_void_p), ("stage1_out", _c_void_p), ("out", _c_void_p),
-                ("dbg_nbr_q", _c_void_p), ("dbg_nbr_p", _c_void_p), ("nbr_q", _c_void_p), ("nbr_p", _c_void_p)]
+                ("dbg_nbr_q", _c_void_p), ("dbg_nbr_p", _c_void_p), ("nbr_q", _c_void_p), ("nbr_p", _c_void_p),
+                ("query_begin", _c_ll), ("query_end", _c_ll)]
 
 
 class RowMlpPhase(ctypes.Structure):

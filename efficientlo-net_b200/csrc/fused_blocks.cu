@@ -142,7 +142,7 @@ __global__ void __launch_bounds__(LAUNCH_THREADS, 1) group_mlp_max_kernel(const 
 struct Cv1Params {
     QuerySet qs;
     Window g;
-    long long total_q;
+    long long q_first, total_q;      // pixels [q_first, total_q) are this call's queries
     int qt, C, total_chunks, nring;
     int sl_in_ring;      // tensor-core engine: the logits' pool staging aliases the (by then dead) weight ring
     const float* xyz1;
@@ -218,7 +218,7 @@ __global__ void __launch_bounds__(LAUNCH_THREADS, 1) cost_volume_1_kernel(const 
     for (int i = threadIdx.x; i < RS; i += CTA_THREADS) nbr[i] = -1;
     compute_sync();
 
-    const long long q0 = (long long)blockIdx.x * p.qt;
+    const long long q0 = p.q_first + (long long)blockIdx.x * p.qt;
     const int cells = g.h2 * g.w2, nwarps = COMPUTE_WARPS;
     float* sdist = A;
     int* shw = reinterpret_cast<int*>(A + (size_t)nwarps * g.kt);
@@ -281,7 +281,7 @@ __global__ void __launch_bounds__(LAUNCH_THREADS, 1) cost_volume_1_kernel(const 
 struct Cv2Params {
     QuerySet qs;
     Window g;
-    long long total_q;
+    long long q_first, total_q;      // pixels [q_first, total_q) are this call's queries
     int qt, C, total_chunks, nring;
     int sl_in_ring;      // tensor-core engine: logits staged in the dead weight ring, values pooled straight from X
     const float* xyz1;
@@ -325,7 +325,7 @@ __global__ void __launch_bounds__(LAUNCH_THREADS, 1) cost_volume_2_kernel(const 
     for (int i = threadIdx.x; i < RS; i += CTA_THREADS) nbr[i] = -1;
     compute_sync();
 
-    const long long q0 = (long long)blockIdx.x * p.qt;
+    const long long q0 = p.q_first + (long long)blockIdx.x * p.qt;
     const int cells = g.h2 * g.w2;
     if (p.nbr_in != nullptr) tile_load_nbr(p.qs, g.K, p.xyz1, p.nbr_in, q0, p.qt, p.total_q, nbr, ctr);
     else tile_search<false>(p.qs, g, p.xyz1, p.xyz1, off, q0, p.qt, p.total_q, nbr, ctr, nullptr, nullptr);
@@ -729,7 +729,7 @@ __global__ void __launch_bounds__(TC_LAUNCH_THREADS, 2) cost_volume_1_tc_kernel(
     const Window g = p.g;
     const TcRows rows(g.K);
     int* nbr = sm.nbr; float* ctr = sm.ctr; float* X = sm.X;
-    const long long q0 = (long long)blockIdx.x * p.qt;
+    const long long q0 = p.q_first + (long long)blockIdx.x * p.qt;
     const int cells = g.h2 * g.w2;
     pdl_trigger();
     TcPipe pipe;
@@ -844,7 +844,7 @@ __global__ void __launch_bounds__(TC_LAUNCH_THREADS, 2) cost_volume_2_tc_kernel(
     const Window g = p.g;
     const TcRows rows(g.K);
     int* nbr = sm.nbr; float* ctr = sm.ctr; float* X = sm.X;
-    const long long q0 = (long long)blockIdx.x * p.qt;
+    const long long q0 = p.q_first + (long long)blockIdx.x * p.qt;
     const int cells = g.h2 * g.w2;
     pdl_trigger();
     TcPipe pipe;
@@ -1224,7 +1224,15 @@ extern "C" int elo_group_mlp_max(const elo_group_mlp_desc* d, void* stream)
     GroupMlpParams p;
     p.qs = make_queries(&d->queries);
     p.g = make_window(&d->window[0]);
-    const long long per_set = (long long)d->batch_size * p.qs.oh * p.qs.ow;
+    long long per_set = (long long)d->batch_size * p.qs.oh * p.qs.ow;
+    long long qb = 0;                        // optional sub-range of each set's queries (row bands)
+    if (d->query_begin != 0 || d->query_end != 0) {
+        if (d->query_begin < 0 || d->query_end > per_set || d->query_begin > d->query_end)
+            return set_error(ELO_ERR_INVALID_ARGUMENT, "group_mlp_max: bad query range");
+        qb = d->query_begin;
+        per_set = d->query_end - d->query_begin;
+        if (per_set == 0) return ELO_OK;
+    }
     p.Cf = d->feat_channels;
     p.nl = d->num_layers;
     int cin = 3 + p.Cf, chunks = 0;
@@ -1241,7 +1249,7 @@ extern "C" int elo_group_mlp_max(const elo_group_mlp_desc* d, void* stream)
         p.feat2[s] = d->feat2[u]; p.random_hw[s] = d->window[u].random_hw; p.weights[s] = d->weights[u];
         p.out[s] = d->out[u]; p.dbg_nbr[s] = d->dbg_nbr[u]; p.nbr_in[s] = d->nbr[u]; p.tlog = g_tlog;
         if (d->set_batch_offset[u] < 0) return set_error(ELO_ERR_INVALID_ARGUMENT, "group_mlp_max: negative batch offset");
-        p.q_base[s] = (long long)d->set_batch_offset[u] * p.qs.oh * p.qs.ow;
+        p.q_base[s] = (long long)d->set_batch_offset[u] * p.qs.oh * p.qs.ow + qb;
         p.q_end[s] = p.q_base[s] + per_set;
     }
     const int kt = p.g.kt, xch = (3 + p.Cf + 3) & ~3;
@@ -1295,6 +1303,14 @@ extern "C" int elo_cost_volume_1(const elo_cost_volume_desc* d, void* stream)
     p.qs.H1 = d->H; p.qs.W1 = d->W; p.qs.oh = d->H; p.qs.ow = d->W; p.qs.qs_h = 1; p.qs.qs_w = 1;
     p.g = make_window(&d->window_q);
     p.total_q = (long long)d->batch_size * d->H * d->W;
+    p.q_first = 0;
+    if (d->query_begin != 0 || d->query_end != 0) {      // a sub-range of the pixels (row bands)
+        if (d->query_begin < 0 || d->query_end > p.total_q || d->query_begin > d->query_end)
+            return set_error(ELO_ERR_INVALID_ARGUMENT, "cost_volume: bad query range");
+        p.q_first = d->query_begin;
+        p.total_q = d->query_end;
+        if (p.q_first == p.total_q) return ELO_OK;
+    }
     p.C = d->C;
     const int xc = 10 + 2 * d->C;
     p.total_chunks = layer_chunks(xc, 128) + layer_chunks(128, 64) + layer_chunks(64, 64) + layer_chunks(10, 64) +
@@ -1316,7 +1332,7 @@ extern "C" int elo_cost_volume_1(const elo_cost_volume_desc* d, void* stream)
             p.nring = tc_pick_ring(base, p.total_chunks);
         }
         if (p.nring < 2) return set_error(ELO_ERR_UNSUPPORTED, "cost_volume_1: tile does not fit shared memory");
-        const TcChoice tc = choose_tc_tile(p.total_q, p.g.K, 1, p.sl_in_ring ? 2 : 1);
+        const TcChoice tc = choose_tc_tile(p.total_q - p.q_first, p.g.K, 1, p.sl_in_ring ? 2 : 1);
         p.qt = tc.per_tile;
         p.g.kt = 0;
         return launch_tc(cost_volume_1_tc_kernel, p, dim3(tc.tiles), base + (size_t)p.nring * TC_CHUNK_BYTES,
@@ -1327,7 +1343,7 @@ extern "C" int elo_cost_volume_1(const elo_cost_volume_desc* d, void* stream)
         if ((size_t)kt * 64 > (size_t)320 * 64 * nb * 4) return (size_t)1 << 30;
         return common_smem(kt, 64 * nb) + (size_t)(xch + 320) * 64 * nb * 4;
     };
-    const TileChoice tc = choose_tile(p.total_q, p.g.K, 1, smem);
+    const TileChoice tc = choose_tile(p.total_q - p.q_first, p.g.K, 1, smem);
     if (tc.nb == 0) return set_error(ELO_ERR_UNSUPPORTED, "cost_volume_1: tile does not fit shared memory");
     p.qt = tc.per_tile;
     p.nring = pick_ring(smem(tc.nb), p.total_chunks);
@@ -1360,6 +1376,14 @@ extern "C" int elo_cost_volume_2(const elo_cost_volume_desc* d, void* stream)
     p.qs.H1 = d->H; p.qs.W1 = d->W; p.qs.oh = d->H; p.qs.ow = d->W; p.qs.qs_h = 1; p.qs.qs_w = 1;
     p.g = make_window(&d->window_p);
     p.total_q = (long long)d->batch_size * d->H * d->W;
+    p.q_first = 0;
+    if (d->query_begin != 0 || d->query_end != 0) {      // a sub-range of the pixels (row bands)
+        if (d->query_begin < 0 || d->query_end > p.total_q || d->query_begin > d->query_end)
+            return set_error(ELO_ERR_INVALID_ARGUMENT, "cost_volume: bad query range");
+        p.q_first = d->query_begin;
+        p.total_q = d->query_end;
+        if (p.q_first == p.total_q) return ELO_OK;
+    }
     p.C = d->C;
     p.total_chunks = layer_chunks(10, 64) + layer_chunks(128 + d->C, 128) + layer_chunks(128, 64);
     p.xyz1 = d->xyz1; p.f1 = d->f1; p.cv1 = d->stage1_out; p.random_hw = d->window_p.random_hw;
@@ -1377,14 +1401,14 @@ extern "C" int elo_cost_volume_2(const elo_cost_volume_desc* d, void* stream)
             p.nring = tc_pick_ring(base, p.total_chunks);
         }
         if (p.nring < 2) return set_error(ELO_ERR_UNSUPPORTED, "cost_volume_2: tile does not fit shared memory");
-        const TcChoice tc = choose_tc_tile(p.total_q, p.g.K, 1, p.sl_in_ring ? 2 : 1);
+        const TcChoice tc = choose_tc_tile(p.total_q - p.q_first, p.g.K, 1, p.sl_in_ring ? 2 : 1);
         p.qt = tc.per_tile;
         p.g.kt = 0;
         return launch_tc(cost_volume_2_tc_kernel, p, dim3(tc.tiles), base + (size_t)p.nring * TC_CHUNK_BYTES,
                          (cudaStream_t)stream, "cost_volume_2 (tensor core) launch");
     }
     auto smem = [&](int nb) { return common_smem(kt, 64 * nb) + (size_t)(12 + 128 + d->C + 192) * 64 * nb * 4; };
-    const TileChoice tc = choose_tile(p.total_q, p.g.K, 1, smem);
+    const TileChoice tc = choose_tile(p.total_q - p.q_first, p.g.K, 1, smem);
     if (tc.nb == 0) return set_error(ELO_ERR_UNSUPPORTED, "cost_volume_2: tile does not fit shared memory");
     p.qt = tc.per_tile;
     p.nring = pick_ring(smem(tc.nb), p.total_chunks);

@@ -130,7 +130,8 @@ struct SearchSpec {
     QuerySet qs;
     Window g;
     int select, fast_ok;
-    long long total_q;        // batch * oh * ow
+    long long q_first;        // queries [q_first, total_q) of the batch * oh * ow are searched
+    long long total_q;
     int cta_begin;            // first CTA of this spec
     const float* xyz1;
     const float* xyz2;
@@ -161,7 +162,7 @@ __global__ void __launch_bounds__(256) multi_search_kernel(const __grid_constant
     const int nq = sp.qs.oh * sp.qs.ow;
     const int cta_end = (si + 1 < p.nspec) ? p.spec[si + 1].cta_begin : (int)gridDim.x;
     const int ctas = cta_end - sp.cta_begin;
-    for (long long q = (long long)((int)blockIdx.x - sp.cta_begin) * nwarps + warp; q < sp.total_q;
+    for (long long q = sp.q_first + (long long)((int)blockIdx.x - sp.cta_begin) * nwarps + warp; q < sp.total_q;
          q += (long long)ctas * nwarps) {
         int* row = sp.out_nbr + q * g.K;
         for (int k = lane; k < g.K; k += 32) row[k] = -1;
@@ -317,8 +318,16 @@ extern "C" int elo_multi_search(const elo_search_desc* specs, int nspec, void* s
         sp.select = d->select ? 1 : 0;
         sp.fast_ok = (w->K <= 32 && sp.g.d2max < 1e10f) ? 1 : 0;
         sp.total_q = (long long)d->batch_size * sp.qs.oh * sp.qs.ow;
+        sp.q_first = 0;
+        if (d->query_begin != 0 || d->query_end != 0) {
+            if (d->query_begin < 0 || d->query_end > sp.total_q || d->query_begin > d->query_end)
+                return set_error(ELO_ERR_INVALID_ARGUMENT, "multi_search: bad query range");
+            sp.q_first = d->query_begin;
+            sp.total_q = d->query_end;
+            if (sp.q_first == sp.total_q) { --p.nspec; continue; }
+        }
         sp.xyz1 = d->xyz1; sp.xyz2 = d->xyz2; sp.random_hw = w->random_hw; sp.out_nbr = d->out_nbr;
-        long long ctas = (sp.total_q + warps - 1) / warps;
+        long long ctas = (sp.total_q - sp.q_first + warps - 1) / warps;
         const long long cap = (long long)sms * 8;
         if (ctas > cap) ctas = cap;
         sp.cta_begin = (int)ctas_total;

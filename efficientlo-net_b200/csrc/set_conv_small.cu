@@ -228,12 +228,20 @@ extern "C" int elo_set_conv_small(const elo_group_mlp_desc* d, void* stream)
     p.g.kt = w->kernel_size_H * w->kernel_size_W; p.g.stride_h = w->stride_h; p.g.stride_w = w->stride_w;
     p.g.K = w->K; p.g.flag_copy = 0; p.g.d2max = w->distance * w->distance;
     p.per_set = (long long)d->batch_size * p.qs.oh * p.qs.ow;
+    long long qb = 0;                        // optional sub-range of each set's queries (row bands)
+    if (d->query_begin != 0 || d->query_end != 0) {
+        if (d->query_begin < 0 || d->query_end > p.per_set || d->query_begin > d->query_end)
+            return set_error(ELO_ERR_INVALID_ARGUMENT, "set_conv_small: bad query range");
+        qb = d->query_begin;
+        p.per_set = d->query_end - d->query_begin;
+        if (p.per_set == 0) return ELO_OK;
+    }
     for (int s = 0; s < 2; ++s) {
         const int u = s < d->nsets ? s : 0;
         if (!d->window[u].random_hw || d->set_batch_offset[u] < 0)
             return set_error(ELO_ERR_INVALID_ARGUMENT, "set_conv_small: bad parameter set");
         p.random_hw[s] = d->window[u].random_hw;
-        p.q_base[s] = (long long)d->set_batch_offset[u] * p.qs.oh * p.qs.ow;
+        p.q_base[s] = (long long)d->set_batch_offset[u] * p.qs.oh * p.qs.ow + qb;
     }
     p.xyz = d->xyz1; p.feat = d->feat2[0]; p.weights = d->weights[0];
     p.out = d->out[0]; p.dbg_nbr = d->dbg_nbr[0]; p.nbr_in = d->nbr[0];

@@ -25,12 +25,14 @@ def _order_after_producer(stream, device, *tensors):
 
 class PWCLOEngine:
     def __init__(self, batch_size, H_input=64, W_input=1800, num_points=150000, params=None, perms=None,
-                 device="cuda:0", use_graph=True, packed=False):
+                 device="cuda:0", use_graph=True, packed=False, band=None):
         """packed=False: the static input buffer has the reference's placeholder shape (B, 2N, 6) (pwclo_model.py:19).
         packed=True: it is (B, 2N, 3) -- xyz only, the 12 of 24 bytes per point the path reads -- and load() also
         accepts the two frames as (B, n1, 3) / (B, n2, 3) prefixes without their zero padding (the padding is done on
         the device: rows past the prefix stay, or are reset to, zero)."""
         self.B, self.H, self.W, self.N = batch_size, H_input, W_input, num_points
+        self.band = band              # pwclo_model.RowBand: this engine computes one row band of every pair (B = 1);
+                                      # all ranks of the band's group must load the same pair and call run() together
         self.packed = bool(packed)
         self.filled = [0, 0]          # rows of each frame's slab that may hold points (packed prefix uploads)
         self.device = torch.device(device)
@@ -51,7 +53,7 @@ class PWCLOEngine:
         prev, self.store.scratch_ns = self.store.scratch_ns, id(self)
         try:
             return pwclo_model.get_model(self.pc, self.H, self.W, self.T_gt, None, None, False, params=self.store,
-                                         perms=self.perms)
+                                         perms=self.perms, band=self.band)
         finally:
             self.store.scratch_ns = prev
 

@@ -78,8 +78,9 @@ def projection_constants(H_input, W_input):
 
 def _scratch(name, shape, dtype, device, fill=None):
     """Persistent scratch from the current store if there is one, else a fresh tensor."""
-    if _store._current:
-        return _store._current[-1].scratch(name, shape, dtype, fill=fill)
+    stack = _store.current_stack()
+    if stack:
+        return stack[-1].scratch(name, shape, dtype, fill=fill)
     t = torch.empty(shape, dtype=dtype, device=device)
     if fill is not None:
         t.fill_(fill)

@@ -92,11 +92,13 @@ def _f32(t):
 
 
 # ----------------------------------------------------------------------------------------------
-def search_spec(select, xyz1, xyz2, queries, kernel_size, K, distance, stride_h, stride_w, random_hw, out=None):
+def search_spec(select, xyz1, xyz2, queries, kernel_size, K, distance, stride_h, stride_w, random_hw, out=None,
+                qrange=None):
     """One entry for multi_search.  queries = (out_h, out_w, q_stride_h, q_stride_w) inside xyz1's image;
-    `out` an optional pre-allocated (B, out_h*out_w, K) int32 view to write into."""
+    `out` an optional pre-allocated (B, out_h*out_w, K) int32 view to write into; `qrange` = (begin, end): only
+    these linear queries are searched (row bands), the other rows of the table are left untouched."""
     return dict(select=select, xyz1=xyz1, xyz2=xyz2, queries=queries, kernel_size=kernel_size, K=K,
-                distance=distance, stride_h=stride_h, stride_w=stride_w, random_hw=random_hw, out=out)
+                distance=distance, stride_h=stride_h, stride_w=stride_w, random_hw=random_hw, out=out, qrange=qrange)
 
 
 def multi_search(specs):
@@ -122,6 +124,8 @@ def multi_search(specs):
         d.window = _window(sp["kernel_size"], sp["K"], sp["distance"], sp["stride_h"], sp["stride_w"],
                            xyz2.shape[1], xyz2.shape[2], perm)
         d.xyz1, d.xyz2, d.out_nbr = xyz1.data_ptr(), xyz2.data_ptr(), out.data_ptr()
+        if sp.get("qrange") is not None:
+            d.query_begin, d.query_end = int(sp["qrange"][0]), int(sp["qrange"][1])
         outs.append(out)
         keep += [xyz1, xyz2, perm]
     with torch.cuda.device(dev):
@@ -131,7 +135,7 @@ def multi_search(specs):
 
 
 def set_conv(xyz_proj, points_proj, sel, K_sample, kernel_size, distance, layer_scopes, store, random_hws,
-             feat_channels=None, set_batch_offsets=(0,), debug=None, nbr=None):
+             feat_channels=None, set_batch_offsets=(0,), debug=None, nbr=None, qrange=None):
     """Set-conv kernel launch shared by down_conv and the batched pyramid of pwclo_model.
 
     xyz_proj (Bt, H, W, 3), points_proj (Bt, H, W, C) or None (zero features); ``sel`` a SelectedIdx
@@ -176,6 +180,8 @@ def set_conv(xyz_proj, points_proj, sel, K_sample, kernel_size, distance, layer_
         d.out[s] = out.data_ptr()
         d.dbg_nbr[s] = _lib.ptr(dbg)
         d.nbr[s] = _lib.ptr(nbr)
+    if qrange is not None:          # only these queries of every set (row bands); other output rows are not written
+        d.query_begin, d.query_end = int(qrange[0]), int(qrange[1])
     _lib.call("elo_group_mlp_max" if big else "elo_set_conv_small", d, dev)
     if debug is not None:
         debug["nbr"] = dbg
@@ -204,7 +210,7 @@ def down_conv(xyz_proj, points_proj, selected_idx, K_sample, kernel_size, distan
 
 # ----------------------------------------------------------------------------------------------
 def up_conv_group(xyz1_proj, xyz2_proj, feat2_projs, kernel_size, stride_h, stride_w, nsample, distance,
-                  scopes_per_set, store, random_hws, debug=None, nbrs=None):
+                  scopes_per_set, store, random_hws, debug=None, nbrs=None, qrange=None):
     """First half of set-upconv for one or two parameter sets in one launch: random-K (with stride)
     neighbours of every dense pixel in the sparse grid, [xyz_diff, feat2] -> up_1_* -> * mask -> max."""
     _lib.require_cuda("up_conv", xyz1_proj, xyz2_proj, *feat2_projs)
@@ -239,18 +245,24 @@ def up_conv_group(xyz1_proj, xyz2_proj, feat2_projs, kernel_size, stride_h, stri
         d.out[s] = outs[u].data_ptr()
         d.dbg_nbr[s] = _lib.ptr(dbgs[u])
         d.nbr[s] = _lib.ptr(nbrs[u]) if nbrs is not None else None
+    if qrange is not None:
+        d.query_begin, d.query_end = int(qrange[0]), int(qrange[1])
     _lib.call("elo_group_mlp_max", d, dev)
     if debug is not None:
         debug["nbr"] = dbgs
     return outs
 
 
-def row_mlp(rows, phases, weights_per_set, out_channels, device, want_phase0=False, phase0_channels=0):
+def row_mlp(rows, phases, weights_per_set, out_channels, device, want_phase0=False, phase0_channels=0, rrange=None,
+            outs=None):
     """Launch elo_row_mlp.  phases: list of dicts(sources=[per-set list of tensors or None for
-    'previous phase'], channels=[...], couts=[...]).  Returns (outs per set, phase-0 outs per set)."""
+    'previous phase'], channels=[...], couts=[...]).  Returns (outs per set, phase-0 outs per set).
+    `rrange` = (begin, end): only these rows are computed (rows are independent; the rest of the outputs is left
+    untouched); `outs`: optional pre-allocated (rows, out_channels) tensors per set."""
     nsets = len(weights_per_set)
+    r0, r1 = (0, int(rows)) if rrange is None else (int(rrange[0]), int(rrange[1]))
     d = _lib.RowMlpDesc()
-    d.rows = int(rows)
+    d.rows = r1 - r0
     d.nsets = nsets
     d.num_phases = len(phases)
     keep = []
@@ -268,18 +280,20 @@ def row_mlp(rows, phases, weights_per_set, out_channels, device, want_phase0=Fal
                 else:
                     t = _f32(src[min(s, len(src) - 1)])
                     keep.append(t)
-                    f.src[s][i] = t.data_ptr()
+                    f.src[s][i] = t.data_ptr() + r0 * int(c) * 4
         for i, c in enumerate(spec["couts"]):
             f.cout[i] = int(c)
-    outs = [torch.empty((rows, out_channels), dtype=torch.float32, device=device) for _ in range(nsets)]
+    if outs is None:
+        outs = [torch.empty((rows, out_channels), dtype=torch.float32, device=device) for _ in range(nsets)]
     p0 = [torch.empty((rows, phase0_channels), dtype=torch.float32, device=device) if want_phase0 else None
           for _ in range(nsets)]
     for s in range(2):
         u = min(s, nsets - 1)
         d.weights[s] = weights_per_set[u].data_ptr()
-        d.out[s] = outs[u].data_ptr()
-        d.out_phase0[s] = _lib.ptr(p0[u])
-    _lib.call("elo_row_mlp", d, device)
+        d.out[s] = outs[u].data_ptr() + r0 * out_channels * 4
+        d.out_phase0[s] = (p0[u].data_ptr() + r0 * phase0_channels * 4) if p0[u] is not None else None
+    if d.rows > 0:
+        _lib.call("elo_row_mlp", d, device)
     return outs, p0
 
 
@@ -309,7 +323,7 @@ def up_conv(xyz1_proj, xyz2_proj, feat1_proj, feat2_proj, kernel_size, stride_h,
 def cost_volume(warped_xyz1_proj, xyz2_proj, points1_proj, points2_proj, kernel_size1, kernel_size2, nsample,
                 nsample_q, distance, mlp1, mlp2, is_training, bn_decay, scope, bn=True, pooling='max', knn=True,
                 corr_func='elementwise_product', random_hw_q=None, random_hw_p=None, params=None, debug=None,
-                nbr_q=None, nbr_p=None):
+                nbr_q=None, nbr_p=None, qrange1=None, qrange2=None):
     """Two-stage attentive cost volume (utils/pointnet_util.py:33-149).  Stage 1 correlates every
     (warped) frame-1 pixel with its nsample_q nearest frame-2 pixels inside kernel_size2 (select-K,
     distance fixed at 1000 as in :51); stage 2 aggregates the stage-1 embeddings of nsample frame-1
@@ -350,7 +364,11 @@ def cost_volume(warped_xyz1_proj, xyz2_proj, points1_proj, points2_proj, kernel_
     d.stage1_out, d.out = stage1.data_ptr(), out.data_ptr()
     d.dbg_nbr_q, d.dbg_nbr_p = _lib.ptr(dq), _lib.ptr(dp)
     d.nbr_q, d.nbr_p = _lib.ptr(nbr_q), _lib.ptr(nbr_p)
+    # row bands: stage 1 on qrange1 (the band plus the rows stage 2's window reaches into), stage 2 on qrange2
+    if qrange1 is not None:
+        d.query_begin, d.query_end = int(qrange1[0]), int(qrange1[1])
     _lib.call("elo_cost_volume_1", d, dev)
+    d.query_begin, d.query_end = (0, 0) if qrange2 is None else (int(qrange2[0]), int(qrange2[1]))
     _lib.call("elo_cost_volume_2", d, dev)
     if debug is not None:
         debug.update(nbr_q=dq, nbr_p=dp, stage1=stage1)

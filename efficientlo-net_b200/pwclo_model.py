@@ -52,8 +52,52 @@ def _heads(store, lvl):
     return tuple(out)
 
 
+class RowBand:
+    """Row-band partition of ONE frame pair over the ranks of a process group (BASELINE.json north_star, SURVEY.md
+    section 8(e)).  Rank r owns image rows [r0, r1) of every banded level.  The heavy blocks of a banded level --
+    the level's four neighbour searches, both stages of the cost volume, both set-upconvs and the predictors, and
+    layer 0 of the feature pyramid -- run only for the queries of the owned rows (`query_begin / query_end` of the
+    C ABI); what they read (the level's grids, the coarser level's embeddings) is held in full by every rank, so
+    the window of a query never needs rows that are not there and no halo has to be fetched.  ONE all-gather per
+    banded block chain then makes the level's result complete on every rank again: per level the rows of
+    (embedding, mask logits), once for layer 0 the rows of both frames' features.  Small levels are computed
+    by every rank (they are a handful of single-wave kernels; exchanging them would cost more than computing them).
+    """
+
+    def __init__(self, rank, world, group=None, min_rows_per_rank=2, skip=()):
+        self.rank, self.world, self.group, self.min_rows = int(rank), int(world), group, int(min_rows_per_rank)
+        self.skip = set(skip)         # tags ("layer0", "l0", "l1", "l2") that are NOT banded
+        self.exchanges = 0
+
+    def rows(self, h, tag=None):
+        """(r0, r1) of an h-row level for this rank, or None when the level is not banded (rows do not divide evenly
+        over the ranks, bands would be thinner than min_rows_per_rank, or the level's tag is in `skip`)."""
+        if self.world <= 1 or h % self.world or h // self.world < self.min_rows or tag in self.skip:
+            return None
+        per = h // self.world
+        return self.rank * per, (self.rank + 1) * per
+
+    def gather_rows(self, tensors, h, w):
+        """tensors: list of (S, h*w, C) tensors whose rows [r0*w, r1*w) this rank has just computed.  After the call
+        every rank holds all rows of all of them: one all-gather (NCCL over NVLink) of the rank's slabs."""
+        import torch.distributed as dist
+        per = h // self.world
+        r0, r1 = self.rank * per, (self.rank + 1) * per
+        n = per * w
+        send = torch.cat([t[:, r0 * w:r1 * w].reshape(-1) for t in tensors])
+        recv = torch.empty((self.world, send.numel()), dtype=send.dtype, device=send.device)
+        dist.all_gather_into_tensor(recv, send, group=self.group)
+        off = 0
+        for t in tensors:
+            S, _, C = t.shape
+            part = recv[:, off:off + S * n * C].view(self.world, S, n, C)
+            t.view(S, self.world, n, C).copy_(part.permute(1, 0, 2, 3))
+            off += S * n * C
+        self.exchanges += 1
+
+
 def get_model(point_cloud, H_input, W_input, T_gt, T_trans, T_trans_inv, is_training, bn_decay=None,
-              params=None, perms=None, aug_frame=None, keep=None):
+              params=None, perms=None, aug_frame=None, keep=None, band=None):
     """Whole network (pwclo_model.py:30-433).
 
     point_cloud (B, 2*N, 6) fp32 on the GPU, frame 1 in rows [0,N), frame 2 in [N,2N), xyz in channels
@@ -61,6 +105,8 @@ def get_model(point_cloud, H_input, W_input, T_gt, T_trans, T_trans_inv, is_trai
     (params.py); ``perms``: scan orders per call site (params.make_perms) -- the reference redraws them
     every run; ``aug_frame``: which frame each sample augments (the reference draws it with numpy at
     graph-build time, :59; default 2).  ``keep``: optional dict that receives named intermediates.
+    ``band``: a RowBand -- this rank computes only its row band of the banded levels (B must be 1) and the ranks
+    exchange the bands; every rank returns the same poses as a single-GPU call.
     Returns (l0_q, l0_t, l1_q, l1_t, l2_q, l2_t, l3_q, l3_t, l0_xyz_f1, q_gt, t_gt)."""
     if pu._is_training(is_training):
         # batch-statistics batch norm + autograd: the differentiable composition in train_graph.py
@@ -79,6 +125,11 @@ def get_model(point_cloud, H_input, W_input, T_gt, T_trans, T_trans_inv, is_trai
     oh, ow = pyramid_shapes(H_input, W_input)
     K = keep if keep is not None else {}
     want = keep is not None
+    if band is not None and (B != 1 or want):
+        raise ValueError("row bands shard ONE frame pair (B = 1) and keep no intermediates")
+
+    def band_rows(h, tag):
+        return band.rows(h, tag) if band is not None else None
 
     with use_store(store):
         # ---- PreProcess (:61) + ProjectPC2SphericalRing x2 (:63-64), both frames in one pass.
@@ -119,9 +170,11 @@ def get_model(point_cloud, H_input, W_input, T_gt, T_trans, T_trans_inv, is_trai
             nbr_pyr.append(table)
             for f, half in (("f1", slice(0, B)), ("f2", slice(B, 2 * B))):
                 g_ = grids[l][half]
+                rb = band_rows(oh[l + 2], "layer0") if l == 0 else None
                 specs.append(pu.search_spec(False, g_, g_, (sels[l].out_h, sels[l].out_w, sels[l].stride_h,
                                                             sels[l].stride_w), ks, K_l, DOWN_CONV_DIS[l], 1, 1,
-                                            perms["sa1/layer%d/%s" % (l, f)], out=table[half]))
+                                            perms["sa1/layer%d/%s" % (l, f)], out=table[half],
+                                            qrange=None if rb is None else (rb[0] * ow[l + 2], rb[1] * ow[l + 2])))
         x2f1, x2f2 = xyz[2][:B], xyz[2][B:]
         all2 = (oh[4], ow[4], 1, 1)
         specs.append(pu.search_spec(True, x2f1, x2f2, all2, (5, 35), 32, 1000.0, 1, 1, perms["flow_embedding_l2_origin/q"]))
@@ -139,9 +192,13 @@ def get_model(point_cloud, H_input, W_input, T_gt, T_trans, T_trans_inv, is_trai
             _lib.PROFILE_TAG[0] = "sa%d" % l
             sel = sels[l]
             scopes = ["sa1/layer%d/conv%d" % (l, j) for j in range(3)]
+            rb = band_rows(oh[l + 2], "layer0") if l == 0 else None        # layer 0 (the 64x1800 / 128x2048 image) is banded
+            qr = None if rb is None else (rb[0] * ow[l + 2], rb[1] * ow[l + 2])
             feat = pu.set_conv(src_xyz, src_pts, sel, DOWN_CFG[l][0], DOWN_CFG[l][1], DOWN_CONV_DIS[l], scopes, store,
                                [perms["sa1/layer%d/f1" % l], perms["sa1/layer%d/f2" % l]], feat_channels=src_c,
-                               set_batch_offsets=(0, B), nbr=nbr_pyr[l])
+                               set_batch_offsets=(0, B), nbr=nbr_pyr[l], qrange=qr)
+            if rb is not None:
+                band.gather_rows([feat], oh[l + 2], ow[l + 2])
             pts[l] = feat                                                       # (2B, n_l, C_l)
             src_xyz, src_pts, src_c = xyz[l], feat.view(2 * B, oh[l + 2], ow[l + 2], -1), feat.shape[-1]
             if want:
@@ -188,22 +245,30 @@ def get_model(point_cloud, H_input, W_input, T_gt, T_trans, T_trans_inv, is_trai
             names = ["up_sa_layer_layer_l%dw" % lvl, "up_sa_layer_layer_l%dcostvolume" % lvl]
             allq = (h, w_, 1, 1)
             s_h, s_w = STRIDE_H[lvl + 3], STRIDE_W[lvl + 3]
+            # row band of this rank (None: the level is computed whole).  Stage 2 of the cost volume looks one row up
+            # and down (3x5 window), so stage 1 and its search also cover those two rows; nothing is exchanged for it.
+            rb = band_rows(h, "l%d" % lvl)
+            qr = None if rb is None else (rb[0] * w_, rb[1] * w_)
+            qr1 = None if rb is None else (max(rb[0] - 1, 0) * w_, min(rb[1] + 1, h) * w_)
             nq_, np_, nu0, nu1 = pu.multi_search([
                 pu.search_spec(True, xyz_wp, f2(xyz[lvl]), allq, CV_KERNEL_Q[lvl], 6, 1000.0, 1, 1,
-                               perms["flow_embedding_l%d/q" % lvl]),
+                               perms["flow_embedding_l%d/q" % lvl], qrange=qr1),
                 pu.search_spec(False, xyz_wp, xyz_wp, allq, (3, 5), 4, COST_VOLUME_DIS[lvl], 1, 1,
-                               perms["flow_embedding_l%d/p" % lvl]),
-                pu.search_spec(False, xyz_wp, up_xyz, allq, (7, 15), 8, UP_CONV_DIS[lvl], s_h, s_w, perms[names[0]]),
-                pu.search_spec(False, xyz_wp, up_xyz, allq, (7, 15), 8, UP_CONV_DIS[lvl], s_h, s_w, perms[names[1]])])
+                               perms["flow_embedding_l%d/p" % lvl], qrange=qr),
+                pu.search_spec(False, xyz_wp, up_xyz, allq, (7, 15), 8, UP_CONV_DIS[lvl], s_h, s_w, perms[names[0]],
+                               qrange=qr),
+                pu.search_spec(False, xyz_wp, up_xyz, allq, (7, 15), 8, UP_CONV_DIS[lvl], s_h, s_w, perms[names[1]],
+                               qrange=qr)])
             # cost volume between the warped frame 1 and frame 2 (:242-244)
             cv = pu.cost_volume(xyz_wp, f2(xyz[lvl]), pts_wp, grid(lvl, f2(pts[lvl])), [3, 5], CV_KERNEL_Q[lvl], 4, 6,
                                 COST_VOLUME_DIS[lvl], [128, 64, 64], [128, 64], False, bn_decay,
                                 "flow_embedding_l%d" % lvl, random_hw_q=perms["flow_embedding_l%d/q" % lvl],
-                                random_hw_p=perms["flow_embedding_l%d/p" % lvl], nbr_q=nq_, nbr_p=np_)
+                                random_hw_p=perms["flow_embedding_l%d/p" % lvl], nbr_q=nq_, nbr_p=np_,
+                                qrange1=qr1, qrange2=qr)
             # the two set-upconvs of the level (:247-251) share one launch for their first half ...
             ups = pu.up_conv_group(xyz_wp, up_xyz, [up_w, up_pred], (7, 15), s_h, s_w, 8,
                                    UP_CONV_DIS[lvl], [["%s/up_1_%d" % (n, j) for j in range(2)] for n in names],
-                                   store, [perms[n] for n in names], nbrs=[nu0, nu1])
+                                   store, [perms[n] for n in names], nbrs=[nu0, nu1], qrange=qr)
             # ... and one launch for their second half chained into the two predictors (:253-254)
             rows = B * h * w_
             pts_w = pts_wp.reshape(rows, C)
@@ -213,8 +278,10 @@ def get_model(point_cloud, H_input, W_input, T_gt, T_trans, T_trans_inv, is_trai
                                      "%s/conv_predictor1" % p]) for n, p in zip(names, pred_names)]
             phases = [dict(sources=[[u.reshape(rows, 64) for u in ups], [pts_w]], channels=[64, C], couts=[128, 64]),
                       dict(sources=[[pts_w], None, [cv_r]], channels=[C, 64, 64], couts=[128, 64])]
-            outs, up2 = pu.row_mlp(rows, phases, streams, 64, dev, want_phase0=want, phase0_channels=64)
+            outs, up2 = pu.row_mlp(rows, phases, streams, 64, dev, want_phase0=want, phase0_channels=64, rrange=qr)
             wgt, pred = outs[0].view(B, h * w_, 64), outs[1].view(B, h * w_, 64)
+            if rb is not None:          # the level's one exchange: every rank gets all rows of (mask logits, embedding)
+                band.gather_rows([wgt, pred], h, w_)
             # attention pooling over the valid re-projected pixels + pose refinement (:262-280)
             pose = mu.pose_head_call(pred, wgt, xyz_wp.reshape(B, -1, 3), heads=_heads(store, lvl), coarse=(q, t),
                                      want_pooled=want)

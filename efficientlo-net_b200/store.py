@@ -7,13 +7,27 @@ need are looked up in the store that is current (``with use_store(store):``) und
 Packed, BN-folded device copies are cached per (layer list, device).
 """
 import contextlib
+import threading
 
 import torch
 
 from . import packing
 
-_current = []
-_prefix = []
+
+class _Stacks(threading.local):
+    """The current-store and scope stacks are per host thread: two threads that drive two engines (or two emulated
+    ranks of a row-band group) must not see each other's store -- its scratch buffers would be shared."""
+
+    def __init__(self):
+        self.current, self.prefix = [], []
+
+
+_tls = _Stacks()
+
+
+def current_stack():
+    """The calling thread's stack of stores (innermost last)."""
+    return _tls.current
 
 
 class ParamStore:
@@ -85,30 +99,30 @@ class ParamStore:
 
 @contextlib.contextmanager
 def use_store(store):
-    _current.append(store)
+    _tls.current.append(store)
     try:
         yield store
     finally:
-        _current.pop()
+        _tls.current.pop()
 
 
 def current_store(explicit=None):
     if explicit is not None:
         return explicit
-    if not _current:
+    if not _tls.current:
         raise RuntimeError("no parameter store: wrap the call in `with use_store(ParamStore(params)):` "
                            "or pass params=")
-    return _current[-1]
+    return _tls.current[-1]
 
 
 @contextlib.contextmanager
 def variable_scope(name):
-    _prefix.append(name)
+    _tls.prefix.append(name)
     try:
         yield
     finally:
-        _prefix.pop()
+        _tls.prefix.pop()
 
 
 def scoped(name):
-    return "/".join(_prefix + [name])
+    return "/".join(_tls.prefix + [name])

@@ -126,6 +126,9 @@ typedef struct {
     const float *xyz1;        /* (B, H, W, 3) query image */
     const float *xyz2;        /* (B, small_h, small_w, 3) searched grid */
     int *out_nbr;
+    long long query_begin, query_end;   /* linear queries [begin, end) of the B*out_h*out_w to run (row bands of one
+                                           pair: rows [r0, r1) are queries [r0*out_w, r1*out_w)); 0, 0 = all.  Rows of
+                                           out_nbr outside the range are not touched. */
 } elo_search_desc;
 int elo_multi_search(const elo_search_desc *specs, int nspec, void *stream);
 
@@ -151,6 +154,7 @@ typedef struct {
     float *out[2];
     int *dbg_nbr[2];          /* optional (B, n, K): selected linear cell of the searched grid, -1 = masked */
     const int *nbr[2];        /* optional: tables from elo_multi_search; when given, the kernel does not search */
+    long long query_begin, query_end;   /* queries [begin, end) of each set's batch_size*out_h*out_w to run; 0, 0 = all */
 } elo_group_mlp_desc;
 int elo_group_mlp_max(const elo_group_mlp_desc *desc, void *stream);
 
@@ -172,6 +176,8 @@ typedef struct {
     float *out;               /* (B, H*W, 64) */
     int *dbg_nbr_q, *dbg_nbr_p;
     const int *nbr_q, *nbr_p; /* optional: tables from elo_multi_search (stage 1 / stage 2) */
+    long long query_begin, query_end;   /* pixels [begin, end) of the B*H*W to run in THIS call (stage 2 of a row band
+                                           needs stage 1 on one more row of its 3-row window either side); 0, 0 = all */
 } elo_cost_volume_desc;
 int elo_cost_volume_1(const elo_cost_volume_desc *desc, void *stream);
 int elo_cost_volume_2(const elo_cost_volume_desc *desc, void *stream);
