@@ -418,8 +418,9 @@ def run_rowband(args, rank, world, dev, dist):
         barrier()
     if rank == 0:
         oh, _ = elo.pwclo_model.pyramid_shapes(H_IN, W_IN)
-        banded = ["layer0"] + ["l%d" % lvl for lvl in (0, 1, 2) if elo.RowBand(0, world).rows(oh[lvl + 2]) is not None] \
-            if world > 1 else []
+        _, ow = elo.pwclo_model.pyramid_shapes(H_IN, W_IN)
+        probe = elo.RowBand(0, world)
+        banded = [t for t, l in (("layer0", 0), ("l0", 0), ("l1", 1), ("l2", 2)) if probe.rows(oh[l + 2], t, ow[l + 2]) is not None]
         line = {"metric": METRIC, "value": args.steps / (ms * 1e-3), "unit": "frame-pairs/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
                 "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -443,8 +444,30 @@ def run_rowband(args, rank, world, dev, dist):
                 "roofline": None, "cpu_baseline": None,
                 "mlp_engine": "tcgen05 tf32x3" if elo._lib.mlp_engine() == 1 else "fp32 FFMA"}
         print(json.dumps(line), flush=True)
-    if dist is not None:
+    # captured graphs hold NCCL kernels: release them before the communicator goes away
+    del engines, peng
+    finish(dev, dist)
+
+
+def finish(dev, dist):
+    """Tear down the process group; a rank must never hang the launcher (and the GPU box) after the line is printed."""
+    import gc
+    import threading
+    import torch
+    gc.collect()
+    torch.cuda.synchronize(dev)
+    if dist is None:
+        return
+    sys.stdout.flush()
+    sys.stderr.flush()
+    watchdog = threading.Timer(20.0, lambda: os._exit(0))
+    watchdog.daemon = True
+    watchdog.start()
+    try:
+        dist.barrier()
         dist.destroy_process_group()
+    finally:
+        watchdog.cancel()
 
 
 def run_ours(args, rank, world, local_rank):
@@ -689,8 +712,7 @@ def run_ours(args, rank, world, local_rank):
                 "kernel_shares": shares, "roofline": roof, "roofline_index_op": roof_index, "cpu_baseline": cpu,
                 "mlp_engine": "tcgen05 tf32x3" if elo._lib.mlp_engine() == 1 else "fp32 FFMA"}
         print(json.dumps(line), flush=True)
-    if dist is not None:
-        dist.destroy_process_group()
+    finish(dev, dist)
 
 
 def main():

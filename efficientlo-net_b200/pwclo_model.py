@@ -64,15 +64,22 @@ class RowBand:
     by every rank (they are a handful of single-wave kernels; exchanging them would cost more than computing them).
     """
 
-    def __init__(self, rank, world, group=None, min_rows_per_rank=2, skip=()):
+    def __init__(self, rank, world, group=None, min_rows_per_rank=2, min_points=4096, skip=()):
         self.rank, self.world, self.group, self.min_rows = int(rank), int(world), group, int(min_rows_per_rank)
+        # An exchange costs ~25 us (measured, NCCL all-gather inside the captured graph, 2 GPUs); a level with fewer
+        # points than this is a few single-wave kernels that banding does not shorten by that much: at 128x2048 layer 0
+        # and level 0 (8192 points each) are banded, at 64x1800 (3600 points) nothing is.
+        self.min_points = int(min_points)
         self.skip = set(skip)         # tags ("layer0", "l0", "l1", "l2") that are NOT banded
         self.exchanges = 0
 
-    def rows(self, h, tag=None):
-        """(r0, r1) of an h-row level for this rank, or None when the level is not banded (rows do not divide evenly
-        over the ranks, bands would be thinner than min_rows_per_rank, or the level's tag is in `skip`)."""
+    def rows(self, h, tag=None, w=None):
+        """(r0, r1) of an h-row (w-column) level for this rank, or None when the level is not banded: rows do not
+        divide evenly over the ranks, bands would be thinner than min_rows_per_rank, the level has fewer than
+        min_points points, or its tag is in `skip`."""
         if self.world <= 1 or h % self.world or h // self.world < self.min_rows or tag in self.skip:
+            return None
+        if w is not None and h * w < self.min_points:
             return None
         per = h // self.world
         return self.rank * per, (self.rank + 1) * per
@@ -128,8 +135,8 @@ def get_model(point_cloud, H_input, W_input, T_gt, T_trans, T_trans_inv, is_trai
     if band is not None and (B != 1 or want):
         raise ValueError("row bands shard ONE frame pair (B = 1) and keep no intermediates")
 
-    def band_rows(h, tag):
-        return band.rows(h, tag) if band is not None else None
+    def band_rows(h, tag, w=None):
+        return band.rows(h, tag, w) if band is not None else None
 
     with use_store(store):
         # ---- PreProcess (:61) + ProjectPC2SphericalRing x2 (:63-64), both frames in one pass.
@@ -170,7 +177,7 @@ def get_model(point_cloud, H_input, W_input, T_gt, T_trans, T_trans_inv, is_trai
             nbr_pyr.append(table)
             for f, half in (("f1", slice(0, B)), ("f2", slice(B, 2 * B))):
                 g_ = grids[l][half]
-                rb = band_rows(oh[l + 2], "layer0") if l == 0 else None
+                rb = band_rows(oh[l + 2], "layer0", ow[l + 2]) if l == 0 else None
                 specs.append(pu.search_spec(False, g_, g_, (sels[l].out_h, sels[l].out_w, sels[l].stride_h,
                                                             sels[l].stride_w), ks, K_l, DOWN_CONV_DIS[l], 1, 1,
                                             perms["sa1/layer%d/%s" % (l, f)], out=table[half],
@@ -192,7 +199,7 @@ def get_model(point_cloud, H_input, W_input, T_gt, T_trans, T_trans_inv, is_trai
             _lib.PROFILE_TAG[0] = "sa%d" % l
             sel = sels[l]
             scopes = ["sa1/layer%d/conv%d" % (l, j) for j in range(3)]
-            rb = band_rows(oh[l + 2], "layer0") if l == 0 else None        # layer 0 (the 64x1800 / 128x2048 image) is banded
+            rb = band_rows(oh[l + 2], "layer0", ow[l + 2]) if l == 0 else None        # layer 0 (the 64x1800 / 128x2048 image) is banded
             qr = None if rb is None else (rb[0] * ow[l + 2], rb[1] * ow[l + 2])
             feat = pu.set_conv(src_xyz, src_pts, sel, DOWN_CFG[l][0], DOWN_CFG[l][1], DOWN_CONV_DIS[l], scopes, store,
                                [perms["sa1/layer%d/f1" % l], perms["sa1/layer%d/f2" % l]], feat_channels=src_c,
@@ -247,7 +254,7 @@ def get_model(point_cloud, H_input, W_input, T_gt, T_trans, T_trans_inv, is_trai
             s_h, s_w = STRIDE_H[lvl + 3], STRIDE_W[lvl + 3]
             # row band of this rank (None: the level is computed whole).  Stage 2 of the cost volume looks one row up
             # and down (3x5 window), so stage 1 and its search also cover those two rows; nothing is exchanged for it.
-            rb = band_rows(h, "l%d" % lvl)
+            rb = band_rows(h, "l%d" % lvl, w_)
             qr = None if rb is None else (rb[0] * w_, rb[1] * w_)
             qr1 = None if rb is None else (max(rb[0] - 1, 0) * w_, min(rb[1] + 1, h) * w_)
             nq_, np_, nu0, nu1 = pu.multi_search([

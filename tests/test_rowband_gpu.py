@@ -72,12 +72,12 @@ class ThreadBand:
     same device with its own parameter store; gather_rows hands the owned rows to the other threads."""
 
     def __init__(self, elo, rank, world, shared, barrier, skip=()):
-        self.inner = elo.RowBand(rank, world, skip=skip)
+        self.inner = elo.RowBand(rank, world, skip=skip, min_points=0)       # band every level whose rows divide
         self.rank, self.world, self.shared, self.barrier = rank, world, shared, barrier
         self.exchanges = 0
 
-    def rows(self, h, tag=None):
-        return self.inner.rows(h, tag)
+    def rows(self, h, tag=None, w=None):
+        return self.inner.rows(h, tag, w)
 
     def gather_rows(self, tensors, h, w):
         self.shared[self.rank] = tensors
