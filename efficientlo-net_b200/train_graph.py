@@ -82,25 +82,51 @@ class TrainableParams:
         return {n: x.detach().cpu().clone() for n, x in self.t.items()}
 
 
+class _Linear(torch.autograd.Function):
+    """y = x @ W + b on (rows, Cin) with a weight gradient that fills the GPU.  rows is ~10^5..10^6 and Cin, Cout
+    <= 192, so dW = x^T @ dy is a tiny output with an enormous reduction dimension: cuBLAS runs it on a handful of
+    CTAs (the largest single item of the eager step's GPU time).  Here the rows are cut into S slabs, one batched
+    GEMM gives S partial (Cin, Cout) products and their sum is dW -- the same fp32 arithmetic, S-fold parallelism."""
+
+    @staticmethod
+    def forward(ctx, x, w, b):
+        ctx.save_for_backward(x, w)
+        return torch.addmm(b, x, w)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w = ctx.saved_tensors
+        dy = dy.contiguous()
+        dx = dy @ w.t() if ctx.needs_input_grad[0] else None
+        rows = x.shape[0]
+        S = max(1, min(256, rows // 4096))
+        r0 = (rows // S) * S
+        dw = torch.bmm(x[:r0].view(S, r0 // S, -1).transpose(1, 2), dy[:r0].view(S, r0 // S, -1)).sum(0)
+        if r0 < rows:
+            dw = dw + x[r0:].t() @ dy[r0:]
+        return dx, dw, dy.sum(0)
+
+
 class _Net:
     def __init__(self, p, bn_decay, dropout, generator):
         self.p, self.dropout, self.generator = p, dropout, generator
         self.decay = 0.9 if bn_decay is None else float(bn_decay)          # tf_util.py:526
 
     def conv(self, x, scope, relu=True):
-        """1x1 conv + bias + batch-stat BN + ReLU on the last axis (tf_util.py:120-185, 512-531)."""
+        """1x1 conv + bias + batch-stat BN + ReLU on the last axis (tf_util.py:120-185, 512-531).
+        Three kernels forward, three backward: a GEMM with the bias folded in, ONE fused batch-norm kernel (batch
+        mean / biased variance over all rows, normalise, scale and shift, moving averages updated in place with the
+        Bessel-corrected variance -- exactly TF's FusedBatchNorm with updates_collections=None; torch's momentum is
+        1 - decay), ReLU."""
         p = self.p
-        y = x @ p[scope + "/weights"] + p[scope + "/biases"]
-        flat = y.reshape(-1, y.shape[-1])
-        var, mean = torch.var_mean(flat, dim=0, unbiased=False)
-        with torch.no_grad():
-            # FusedBatchNorm hands the moving average the Bessel-corrected variance
-            n = flat.shape[0]
-            mm, mv = p[scope + "/bn/moving_mean"], p[scope + "/bn/moving_variance"]
-            mm.sub_((mm - mean) * (1 - self.decay))
-            mv.sub_((mv - var * (n / max(n - 1, 1))) * (1 - self.decay))
-        y = (y - mean) * torch.rsqrt(var + BN_EPS) * p[scope + "/bn/gamma"] + p[scope + "/bn/beta"]
-        return torch.relu(y) if relu else y
+        w = p[scope + "/weights"]
+        flat = _Linear.apply(x.reshape(-1, x.shape[-1]), w, p[scope + "/biases"])
+        flat = torch.nn.functional.batch_norm(flat, p[scope + "/bn/moving_mean"], p[scope + "/bn/moving_variance"],
+                                              p[scope + "/bn/gamma"], p[scope + "/bn/beta"], training=True,
+                                              momentum=1.0 - self.decay, eps=BN_EPS)
+        if relu:
+            flat = torch.relu_(flat)
+        return flat.view(*x.shape[:-1], w.shape[-1])
 
     def linear(self, x, scope):
         return x @ self.p[scope + "/weights"] + self.p[scope + "/biases"]
@@ -117,7 +143,9 @@ def _gather(grid, nbr):
     B, cells, C = grid.shape
     mask = nbr >= 0
     lin = nbr.clamp(min=0).long() + (torch.arange(B, device=grid.device) * cells).view(B, 1, 1)
-    g = grid.reshape(B * cells, C)[lin.reshape(-1)].view(*nbr.shape, C)
+    # index_select, not advanced indexing: its backward is index_add_ (atomic adds), where the backward of
+    # x[idx] is index_put_(accumulate=True), which sorts the ~10^6 indices of every gather
+    g = grid.reshape(B * cells, C).index_select(0, lin.reshape(-1)).view(*nbr.shape, C)
     return g * mask.unsqueeze(-1), mask.unsqueeze(-1)
 
 
@@ -362,7 +390,7 @@ class Trainer:
 
     def __init__(self, params, batch_size, H_input=64, W_input=1800, optimizer="adam", momentum=0.9,
                  base_lr=BASE_LEARNING_RATE, decay_step=DECAY_STEP, decay_rate=DECAY_RATE, dropout=0.5,
-                 process_group=None, seed=0):
+                 process_group=None, seed=0, use_graph=False):
         self.p, self.batch_size, self.H, self.W = params, batch_size, H_input, W_input
         self.base_lr, self.decay_step, self.decay_rate, self.dropout = base_lr, decay_step, decay_rate, dropout
         if optimizer == "adam":
@@ -373,12 +401,101 @@ class Trainer:
         self.batch = 0
         self.group = process_group
         self.gen = torch.Generator(device=params.device).manual_seed(seed)
+        # whole-step CUDA graph (use_graph=True): forward, loss, backward, gradient all-reduce and the optimizer update
+        # are ~6000 small launches whose issue time, not their run time, bounds the eager step
+        self.use_graph = bool(use_graph)
+        self._graph = None
+        if self.use_graph:
+            if optimizer != "adam":
+                raise ValueError("use_graph needs the capturable Adam")
+            self.opt = torch.optim.Adam(params.parameters(), lr=torch.tensor(base_lr, device=params.device),
+                                        betas=(0.9, 0.999), eps=1e-8, capturable=True)
+
+    # ---- captured step ------------------------------------------------------------------------------------------
+    def _capture(self, point_cloud, T_gt, T_trans, T_trans_inv, perms, bn_decay):
+        from .pwclo_model import get_loss
+        dev = self.p.device
+        st = self._static = dict(pc=point_cloud.detach().to(dev, torch.float32).clone(), T=T_gt.detach().to(dev).float().clone())
+        eye = torch.eye(4, device=dev).expand(point_cloud.shape[0], 4, 4).contiguous()
+        st["Tt"] = (eye if T_trans is None else T_trans.to(dev).float()).clone()
+        st["Ti"] = (eye if T_trans_inv is None else T_trans_inv.to(dev).float()).clone()
+        st["perms"] = {k: torch.as_tensor(v).to(dev, torch.int32).clone() for k, v in perms.items()}
+        self._graph_decay = bn_decay
+
+        def body():
+            out = get_model(st["pc"], self.H, self.W, st["T"], st["Tt"], st["Ti"], self.p, bn_decay=bn_decay,
+                            perms=st["perms"], aug_frame=None, dropout=self.dropout, generator=self.gen)
+            loss = get_loss(*out[:8], out[9], out[10], self.p["w_x"], self.p["w_q"])
+            loss.backward()
+            if self.group is not None:
+                all_reduce_gradients(self.p.parameters(), self.group)
+            self.opt.step()
+            return loss.detach()
+
+        # Warm-up on a side stream (allocator pools, lazily created Adam slots, NCCL communicator) must not count as
+        # training: parameters, moving averages and optimizer slots are put back afterwards, IN PLACE -- the captured
+        # graph refers to these very tensors.
+        snap = {n: t.detach().clone() for n, t in self.p.t.items()}
+        slots = {id(q): {k: v.detach().clone() for k, v in self.opt.state[q].items() if torch.is_tensor(v)}
+                 for q in self.p.parameters() if q in self.opt.state}
+        side = torch.cuda.Stream(dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(2):
+                self.opt.zero_grad(set_to_none=True)
+                body()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        with torch.no_grad():
+            for n, t in self.p.t.items():
+                t.copy_(snap[n])
+            for q in self.p.parameters():
+                for k, v in self.opt.state[q].items():
+                    if torch.is_tensor(v):
+                        old = slots.get(id(q), {}).get(k)
+                        v.copy_(old) if old is not None else v.zero_()
+        self.opt.zero_grad(set_to_none=True)
+        g = torch.cuda.CUDAGraph()
+        g.register_generator_state(self.gen)
+        with torch.cuda.graph(g):
+            self._static_loss = body()
+        self._graph = g
+
+    def _graph_step(self, point_cloud, T_gt, T_trans, T_trans_inv, perms):
+        lr = get_learning_rate(self.batch, self.batch_size, self.base_lr, self.decay_step, self.decay_rate)
+        bn_decay = get_bn_decay(self.batch, self.batch_size, self.decay_step)
+        if perms is None:
+            perms = make_perms(self.batch)
+        if self._graph is None or bn_decay != self._graph_decay:        # the decay is baked into the captured BN kernels
+            self._graph = None
+            for g in self.opt.param_groups:
+                g["lr"].fill_(lr)
+            self._capture(point_cloud, T_gt, T_trans, T_trans_inv, perms, bn_decay)
+        st = self._static
+        st["pc"].copy_(point_cloud, non_blocking=True)
+        st["T"].copy_(T_gt, non_blocking=True)
+        if T_trans is not None:
+            st["Tt"].copy_(T_trans, non_blocking=True)
+            st["Ti"].copy_(T_trans_inv, non_blocking=True)
+        for k, v in perms.items():
+            if v is not st["perms"][k]:
+                st["perms"][k].copy_(torch.as_tensor(v), non_blocking=True)
+        for g in self.opt.param_groups:
+            g["lr"].fill_(lr)
+        self._graph.replay()
+        self.batch += 1
+        return self._static_loss
 
     def step(self, point_cloud, T_gt, T_trans=None, T_trans_inv=None, perms=None, aug_frame=None):
         from .pwclo_model import get_loss
+        if self.use_graph and aug_frame is None:
+            return self._graph_step(point_cloud, T_gt, T_trans, T_trans_inv, perms)
         lr = get_learning_rate(self.batch, self.batch_size, self.base_lr, self.decay_step, self.decay_rate)
         for g in self.opt.param_groups:
-            g["lr"] = lr
+            if torch.is_tensor(g["lr"]):
+                g["lr"].fill_(lr)
+            else:
+                g["lr"] = lr
         out = get_model(point_cloud, self.H, self.W, T_gt, T_trans, T_trans_inv, self.p,
                         bn_decay=get_bn_decay(self.batch, self.batch_size, self.decay_step), perms=perms,
                         aug_frame=aug_frame, dropout=self.dropout, generator=self.gen)

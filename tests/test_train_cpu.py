@@ -75,3 +75,20 @@ def test_gradient_all_reduce_gloo():
         assert torch.equal(a, torch.full((3, 2), 1.5))
         assert torch.equal(b, torch.arange(5.0) * 1.5)
         assert torch.equal(c, torch.tensor([2.0]))
+
+
+def test_slabbed_weight_gradient_is_the_plain_one():
+    """train_graph._Linear: dW as a batched GEMM over row slabs + their sum equals autograd's x^T @ dy (fp32 rounding)."""
+    t = tg()
+    torch.manual_seed(0)
+    for rows in (5, 4096, 10007, 70001):
+        x = torch.randn(rows, 19, requires_grad=True)
+        w = torch.randn(19, 16, requires_grad=True)
+        b = torch.randn(16, requires_grad=True)
+        up = torch.randn(rows, 16)
+        (t._Linear.apply(x, w, b) * up).sum().backward()
+        got = (x.grad.clone(), w.grad.clone(), b.grad.clone())
+        x.grad = w.grad = b.grad = None
+        ((x @ w + b) * up).sum().backward()
+        for g, want in zip(got, (x.grad, w.grad, b.grad)):
+            assert torch.allclose(g, want, rtol=1e-4, atol=1e-4 * float(want.abs().max()))

@@ -24,6 +24,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=2)
     ap.add_argument("--hw", default="64x1800")
+    ap.add_argument("--graph", type=int, default=1, help="1: the whole step replayed as one CUDA graph; 0: eager launches")
     a = ap.parse_args()
     H, W = (int(v) for v in a.hw.split("x"))
     npts = 150000 if H * W <= 150000 else 300000
@@ -38,7 +39,7 @@ def main():
         group = dist.group.WORLD
     tg = elo.train_graph
     tp = tg.TrainableParams(elo.params.init_params(0), dev)
-    tr = tg.Trainer(tp, batch_size=a.batch * world, H_input=H, W_input=W, process_group=group)
+    tr = tg.Trainer(tp, batch_size=a.batch * world, H_input=H, W_input=W, process_group=group, use_graph=bool(a.graph))
     pc, T = elo.synth.synth_batch(a.batch, H, W, npts, seed0=rank * a.batch)
     pc, T = pc.to(dev), T.to(dev)
     perms = elo.params.make_perms(rank)
@@ -62,7 +63,7 @@ def main():
                           "value": a.batch * world / (ms * 1e-3), "unit": "frame-pairs/s", "n_gpus": world,
                           "ms_per_step": ms, "batch_per_gpu": a.batch, "hw": a.hw, "steps": a.steps, "warmup": a.warmup,
                           "loss": float(loss), "peak_mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30,
-                          "scaling": "weak", "collective": "one flat gradient all-reduce per step" if world > 1 else None}))
+                          "scaling": "weak", "step": "one CUDA graph" if a.graph else "eager launches", "collective": "one flat gradient all-reduce per step" if world > 1 else None}))
     if world > 1:
         dist.destroy_process_group()
 
