@@ -164,18 +164,20 @@ def test_graphed_trainer_follows_the_eager_trainer(elo, cuda, pair):
     for use_graph in (False, True):
         tp = tg.TrainableParams(pair["P"], cuda)
         tr = tg.Trainer(tp, batch_size=B, dropout=0.0, use_graph=use_graph)
-        losses = [float(tr.step(pc, T, perms=perms)) for _ in range(2)]
+        losses = [float(tr.step(pc, T, perms=perms))]
+        after_one = tp.export()
+        losses.append(float(tr.step(pc, T, perms=perms)))
         torch.cuda.synchronize()
         assert tr.batch == 2
-        runs.append((losses, tp.export()))
+        runs.append((losses, after_one))
     (le, pe), (lg, pg) = runs
     assert abs(le[0] - lg[0]) <= 2e-6 * abs(le[0]), (le, lg)
     assert abs(le[1] - lg[1]) <= 1e-4 * abs(le[1]) + 1e-5, (le, lg)
     assert le[1] != le[0]
-    # batch-norm moving averages after two steps (not touched by Adam, whose update of a weight with a noise-level
-    # gradient is +-lr whatever the gradient's size, so single weights may differ by 2 lr between any two runs)
+    # after ONE update: the batch-norm moving averages (functions of the initial weights only) agree to rounding, the
+    # weights to Adam's step size (its update of a weight with a noise-level gradient is +-lr whatever the gradient)
     for name in ("sa1/layer0/conv0/bn/moving_mean", "flow_embedding_l0/CV_0/bn/moving_variance",
                  "l0_costvolume_predict/conv_predictor1/bn/moving_variance"):
-        assert torch.allclose(pe[name], pg[name], rtol=2e-3, atol=1e-6), name
+        assert torch.allclose(pe[name], pg[name], rtol=1e-4, atol=1e-6), name
     w = "sa1/layer0/conv0/weights"
-    assert float((pe[w] - pg[w]).abs().max()) <= 2.5 * 1e-3 and not torch.equal(pe[w], pair["P"][w])
+    assert float((pe[w] - pg[w]).abs().max()) <= 2.5e-3 and not torch.equal(pg[w], pair["P"][w])
