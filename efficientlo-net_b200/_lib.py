@@ -67,7 +67,7 @@ class ProjectDesc(ctypes.Structure):
                 ("T", _c_void_p), ("q", _c_void_p), ("t", _c_void_p),
                 ("pi", _c_float), ("az_res", _c_float), ("v_res", _c_float), ("v_off", _c_float),
                 ("cellmin", _c_void_p), ("state", _c_void_p), ("out_xyz", _c_void_p), ("out_feat", _c_void_p), ("out_points", _c_void_p),
-                ("T_apply", _c_void_p), ("out_cell", _c_void_p)]
+                ("T_apply", _c_void_p), ("out_cell", _c_void_p), ("point_keys", _c_void_p)]
 
 
 class PoseHeadDesc(ctypes.Structure):

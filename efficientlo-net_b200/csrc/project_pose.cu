@@ -33,6 +33,7 @@ struct ProjParams {
     unsigned* state;               // [0] epoch of the current call, [1] CTAs of the scatter kernel that are done
     float* out_xyz; float* out_feat; float* out_points;
     int* out_cell;       // optional (B, N): cell of the point if it is (one of) the nearest of its cell, else -1
+    int2* keys;          // optional (B, N): (cell, range bits) of every point, bin kernel -> scatter kernel
 };
 
 __device__ __forceinline__ float mul(float a, float b) { return __fmul_rn(a, b); }
@@ -131,16 +132,29 @@ __global__ void project_bin_kernel(const ProjParams p)
         if (p.out_feat != nullptr)
             for (long long c = i0; c < cells * p.C; c += stride) p.out_feat[c] = 0.f;
     }
+    // A third of a frame's points are zero padding or cropped away: exactly (+0, +0, +0) after the transform.  Their
+    // cell is a constant of the image geometry; one thread per CTA evaluates it with the very arithmetic the other
+    // points go through, and the padding skips atan2 / asin / sqrt / the divisions.
+    __shared__ int s_zero_cell;
+    if (threadIdx.x == 0) {
+        float r0;
+        s_zero_cell = bin_point(p, 0.f, 0.f, 0.f, r0);
+    }
+    __syncthreads();
+    const int zero_cell = s_zero_cell;
     for (long long i = i0; i < total; i += stride) {
         const int b = (int)(i / p.N), n = (int)(i % p.N);
         float x, y, z, r;
         transform_point(p, b, n, x, y, z);
-        const int cell = bin_point(p, x, y, z, r);
+        int cell;
+        if ((__float_as_uint(x) | __float_as_uint(y) | __float_as_uint(z)) == 0u) { cell = zero_cell; r = 0.f; }
+        else cell = bin_point(p, x, y, z, r);
         // r >= 0 (or NaN, which orders above every finite value as an unsigned pattern).  Zero-padded /
         // cropped points all fall into ONE cell per sample with r = 0, the smallest possible key: a plain
         // store is enough for them and avoids ~10^5 serialised atomics on a single address.
         unsigned long long* slot = p.cellmin + (size_t)b * p.H * p.W + cell;
         const unsigned rbits = __float_as_uint(r);
+        if (p.keys != nullptr) p.keys[i] = make_int2(cell, (int)rbits);
         if (rbits == 0u) *slot = cell_key(epoch, 0u);
         else atomicMin(slot, cell_key(epoch, rbits));
         if (p.out_points != nullptr) {
@@ -163,14 +177,23 @@ __global__ void project_scatter_kernel(const ProjParams p)
         const long long pt = i / slabs;
         const int slab = (int)(i - pt * slabs);
         const int b = (int)(pt / p.N), n = (int)(pt % p.N);
-        float x, y, z, r;
-        transform_point(p, b, n, x, y, z);
-        const int cell = bin_point(p, x, y, z, r);
+        float x = 0.f, y = 0.f, z = 0.f, r;
+        int cell;
+        unsigned rbits;
+        if (p.keys != nullptr) {                    // left by the binning pass: no second transform / binning
+            const int2 k = p.keys[pt];
+            cell = k.x; rbits = (unsigned)k.y;
+        } else {
+            transform_point(p, b, n, x, y, z);
+            cell = bin_point(p, x, y, z, r);
+            rbits = __float_as_uint(r);
+        }
         const size_t gcell = (size_t)b * p.H * p.W + cell;
-        const bool winner = cell_key(epoch, __float_as_uint(r)) == p.cellmin[gcell];
+        const bool winner = cell_key(epoch, rbits) == p.cellmin[gcell];
         if (slab == 0 && p.out_cell != nullptr) p.out_cell[pt] = winner ? cell : -1;
         if (!winner) continue;                                       // not the (a) nearest point of its cell
         if (slab == 0) {
+            if (p.keys != nullptr) transform_point(p, b, n, x, y, z);     // winners only: one point per cell
             // equal-range ties accumulate, like scatter_nd (model_util.py:271)
             if (x != 0.f) atomicAdd(p.out_xyz + gcell * 3 + 0, x);
             if (y != 0.f) atomicAdd(p.out_xyz + gcell * 3 + 1, y);
@@ -506,6 +529,7 @@ extern "C" int elo_project(const elo_project_desc* d, void* stream)
     p.cellmin = d->cellmin; p.state = d->state; p.out_xyz = d->out_xyz; p.out_feat = d->feat ? d->out_feat : nullptr;
     p.out_points = d->out_points;
     p.out_cell = d->out_cell;
+    p.keys = reinterpret_cast<int2*>(d->point_keys);
     cudaStream_t st = (cudaStream_t)stream;
     const int sms = device_info().sm_count;
     auto blocks = [&](long long work) {

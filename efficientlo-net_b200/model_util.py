@@ -123,6 +123,8 @@ def project_points(PC, Feature, H_input, W_input, mode=0, T=None, q=None, t=None
     if want_points:
         out_pts = torch.empty((B, N, 3), dtype=torch.float32, device=dev)
         d.out_points = out_pts.data_ptr()
+    keys = _scratch("project_keys_%dx%d" % (B, N), (B, N, 2), torch.int32, dev)      # binning pass -> scatter pass
+    d.point_keys = keys.data_ptr()
     out_cell = None
     if want_cells:
         out_cell = torch.empty((B, N), dtype=torch.int32, device=dev)

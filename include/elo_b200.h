@@ -240,6 +240,9 @@ typedef struct {
     const int *T_apply;       /* optional (B): mode 1 multiplies sample b by T[b] only if T_apply[b] != 0 */
     int *out_cell;            /* optional (B, num_points): cell (row*W+col) if the point is a nearest point of its
                                  cell, else -1 -- lets a differentiable scatter be rebuilt on top (training) */
+    int *point_keys;          /* optional scratch (B, num_points, 2) int32: the binning pass leaves every point's (cell,
+                                 range bits) here and the scatter pass reads them instead of transforming and binning
+                                 the point a second time (atan2, asin, sqrt, divisions) */
 } elo_project_desc;
 int elo_project(const elo_project_desc *desc, void *stream);
 
