@@ -181,6 +181,14 @@ def set_index_kernel(which):
     check(lib().elo_set_index_kernel(int(which)), "elo_set_index_kernel")
 
 
+def set_store_warp_min_cells(min_cells):
+    """Windows of at least this many cells take the select-K kernel with a store warp (0 = always)."""
+    h = lib()
+    h.elo_set_store_warp_min_cells.argtypes = [_c_int]
+    h.elo_set_store_warp_min_cells.restype = _c_int
+    check(h.elo_set_store_warp_min_cells(int(min_cells)), "elo_set_store_warp_min_cells")
+
+
 def set_tile_policy(policy):
     """0: latency (spread small calls over all SMs), 1: throughput (full 128-row tiles)."""
     check(lib().elo_set_tile_policy(int(policy)), "elo_set_tile_policy")

@@ -679,6 +679,7 @@ fused_conv_tiled_kernel(const __grid_constant__ TiledParams p)
 }
 
 static std::atomic<int> g_index_kernel{0};   // 0: by query count, 1: always tiled, 2: always warp-per-query
+static std::atomic<int> g_store_warp_min_kt{getenv("ELO_STORE_WARP_KT") ? atoi(getenv("ELO_STORE_WARP_KT")) : 256};
 
 static unsigned magic_of(unsigned d)
 {
@@ -798,9 +799,9 @@ int launch_index_tiled(bool select, int B, int H, int W, int N, const Window& g,
     // A store warp (one more warp per CTA that writes the count rows while the query warps walk) pays for itself
     // where the walk is long: measured on configs[0]'s frame, 11x41: 171.6 -> 148.7 us; 7x25: 68.3 -> 69.6 us
     // (the query warps drop from 72 to 64 registers, and stores in flight slow the walk's shared-memory loads even
-    // from another warp); 5x15: 45.3 -> 48.0 us.  ELO_STORE_WARP_KT moves the switch-over.
-    static const int sw_min_kt = getenv("ELO_STORE_WARP_KT") ? atoi(getenv("ELO_STORE_WARP_KT")) : 256;
-    const bool sw = select && (out_valid != nullptr || out_vdis != nullptr) && g.kt >= sw_min_kt;
+    // from another warp); 5x15: 45.3 -> 48.0 us.  elo_set_store_warp_min_cells / ELO_STORE_WARP_KT move the switch-over.
+    const bool sw = select && (out_valid != nullptr || out_vdis != nullptr) &&
+                    g.kt >= g_store_warp_min_kt.load(std::memory_order_relaxed);
     auto reg_ctas = [&](int tq) {
         if (!sw) return (select && g.K > 16 ? 512 : 896) / tq;
         if (g.K > 16) return 512 / (tq + 32);
@@ -860,3 +861,12 @@ extern "C" int elo_set_index_kernel(int which)
 }
 
 extern "C" int elo_get_index_kernel(void) { return elo::g_index_kernel.load(std::memory_order_relaxed); }
+
+extern "C" int elo_set_store_warp_min_cells(int min_cells)
+{
+    if (min_cells < 0) return elo::set_error(ELO_ERR_INVALID_ARGUMENT, "elo_set_store_warp_min_cells: >= 0");
+    elo::g_store_warp_min_kt.store(min_cells, std::memory_order_relaxed);
+    return ELO_OK;
+}
+
+extern "C" int elo_get_store_warp_min_cells(void) { return elo::g_store_warp_min_kt.load(std::memory_order_relaxed); }

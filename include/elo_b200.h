@@ -89,6 +89,12 @@ int elo_get_tile_policy(void);
  *                tile-staged thread-per-query kernel (fused_conv_tiled.cu), everything else one warp per query;
  *   1            tiled whenever K <= 32 and distance^2 < 1e10;   2   always one warp per query. */
 int elo_set_index_kernel(int which);
+/* The tile-staged select-K kernel has a form with one extra warp per CTA, the store warp, that writes the CTA's
+ * count rows (valid_idx / valid_in_dis_idx) while the query warps walk their windows.  It is used for windows of
+ * at least `min_cells` cells (default 256: it wins on 11x41, loses a little on 5x15); 0 = always, a huge value =
+ * never.  Results are identical either way. */
+int elo_set_store_warp_min_cells(int min_cells);
+int elo_get_store_warp_min_cells(void);
 int elo_get_index_kernel(void);
 /* Programmatic dependent launch between the kernels of this library (default on; environment ELO_PDL=0
  * turns it off): a kernel's prologue -- barrier / tensor-memory set-up, weight prefetch -- overlaps the

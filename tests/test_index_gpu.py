@@ -13,13 +13,16 @@ pytestmark = pytest.mark.gpu
 GOLDEN = os.path.join(os.path.dirname(__file__), "golden", "index_golden.npz")
 
 
-@pytest.fixture(autouse=True, params=["tiled", "warp"])
+@pytest.fixture(autouse=True, params=["tiled", "tiled+storewarp", "warp"])
 def index_kernel(request, elo):
-    """Every test of this module runs on both work decompositions of the index ops: the tile-staged
-    thread-per-query kernel (fused_conv_tiled.cu) and one warp per query (fused_conv_index.cu)."""
-    elo._lib.set_index_kernel(1 if request.param == "tiled" else 2)
+    """Every test of this module runs on all work decompositions of the index ops: the tile-staged
+    thread-per-query kernel (fused_conv_tiled.cu) without and with its store warp (select-K: one more warp per CTA
+    writes the count rows while the query warps walk), and one warp per query (fused_conv_index.cu)."""
+    elo._lib.set_index_kernel(2 if request.param == "warp" else 1)
+    elo._lib.set_store_warp_min_cells(0 if request.param == "tiled+storewarp" else 1 << 30)
     yield request.param
     elo._lib.set_index_kernel(0)
+    elo._lib.set_store_warp_min_cells(256)
 
 
 def run_cuda(elo, cuda, mode, xyz1, xyz2, idx_n2, random_hw, H, W, npoints, kH, kW, K, flag_copy,
