@@ -92,7 +92,6 @@ SIGNATURES = {
     "elo_row_mlp": [ctypes.POINTER(RowMlpDesc), _c_void_p],
     "elo_project": [ctypes.POINTER(ProjectDesc), _c_void_p],
     "elo_pose_head": [ctypes.POINTER(PoseHeadDesc), _c_void_p],
-    "elo_tc_dense_test": [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_void_p],
     "elo_pyramid_xyz": [_c_int, _c_int, _c_int, ctypes.POINTER(_c_int), ctypes.POINTER(_c_int),
                         ctypes.POINTER(_c_int), ctypes.POINTER(_c_int), _c_void_p, ctypes.POINTER(_c_void_p), _c_void_p],
     "elo_gt_pose": [_c_int, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p],

@@ -71,6 +71,28 @@ def build(force=False, verbose=False):
     return LIB
 
 
+TEST_SRC = os.path.join(os.path.dirname(HERE), "tests", "csrc")
+TEST_LIB = os.path.join(TEST_SRC, "libelo_b200_test.so")
+
+
+def build_test_lib(force=False):
+    """The test hooks of tests/csrc/ (direct doors onto the tcgen05 primitives, used by tests/test_tc_gpu.py and
+    tools/mma_bench.py) as a library of their own: nothing of them is linked into libelo_b200.so."""
+    srcs = sorted(glob.glob(os.path.join(TEST_SRC, "*.cu"))) + [os.path.join(CSRC, "elo_common.cu")]
+    deps = srcs + glob.glob(os.path.join(CSRC, "*.cuh")) + glob.glob(os.path.join(TEST_SRC, "*.h"))
+    if not force and os.path.exists(TEST_LIB) and all(os.path.getmtime(d) <= os.path.getmtime(TEST_LIB) for d in deps):
+        return TEST_LIB
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    env = dict(os.environ)
+    env.pop("CC", None)
+    env.pop("CXX", None)
+    cmd = [nvcc] + NVCC_FLAGS + ["-o", TEST_LIB] + srcs
+    proc = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, env=env)
+    if proc.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + proc.stdout)
+    return TEST_LIB
+
+
 if __name__ == "__main__":
     import sys
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -269,14 +269,6 @@ typedef struct {
 } elo_pose_head_desc;
 int elo_pose_head(const elo_pose_head_desc *desc, void *stream);
 
-/* Test hook for the tensor-core dense layer (tcgen05, 3xTF32): Y[128 x N] = act(X[128 x K] W[K x N] + bias),
- * X, W, Y row-major on the device, K % 16 == 0, K <= 192, N in {64, 128}. */
-int elo_tc_dense_test(const float *X, const float *W, const float *bias, float *Y, int K, int N, int relu,
-                      void *stream);
-
-/* Throughput probe: `iters` tf32 MMAs (128 x N x 8) rotating over `nacc` accumulators; out_cycles[0] (device) = SM cycles. */
-int elo_tc_mma_bench(int N, int iters, int ts, int nacc, long long *out_cycles, void *stream);
-
 /* Strided xyz pyramid (pwclo_model.py:88-114, get_selected_idx + gather_nd): level l of 4 keeps pixel
  * (i*stride_h[l], j*stride_w[l]) of xyz_in (samples,H,W,3) for i < out_h[l], j < out_w[l]; strides are
  * cumulative with respect to xyz_in.  out: 4 device pointers (host array), (samples,out_h[l],out_w[l],3). */

@@ -4,9 +4,10 @@
 #include <cuda_runtime.h>
 
 #include "../../include/elo_b200.h"
-#include "elo_common.cuh"
-#include "elo_mlp.cuh"
-#include "elo_tc.cuh"
+#include "../../efficientlo-net_b200/csrc/elo_common.cuh"
+#include "../../efficientlo-net_b200/csrc/elo_mlp.cuh"
+#include "../../efficientlo-net_b200/csrc/elo_tc.cuh"
+#include "elo_b200_test.h"
 
 namespace elo {
 

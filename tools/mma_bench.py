@@ -2,8 +2,9 @@
 import os, sys, ctypes
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
+import importlib
 import elo_b200 as elo
-lib = elo._lib.lib()
+lib = ctypes.CDLL(importlib.import_module("efficientlo-net_b200.build").build_test_lib())     # tests/csrc hooks
 lib.elo_tc_mma_bench.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
 out = torch.zeros(1, dtype=torch.int64, device="cuda")
 for ts in (1, 2):
