@@ -35,4 +35,15 @@ timeout 600 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytes
     -k "golden or model_sites or unaligned or near_tie or full_frame" > $O/sanitize_index.log 2>&1; echo "memcheck index rc=$?" >> $O/sanitize_index.log
 ELO_STORE_WARP_KT=0 timeout 600 compute-sanitizer --tool memcheck --error-exitcode 9 python tools/index_one.py 7 25 1 > $O/sanitize_storewarp.log 2>&1; echo "memcheck storewarp rc=$?" >> $O/sanitize_storewarp.log
 timeout 600 compute-sanitizer --tool memcheck --error-exitcode 9 python tools/one_forward.py 1 1 > $O/sanitize_forward.log 2>&1; echo "memcheck forward rc=$?" >> $O/sanitize_forward.log
-ls -la $O
+# gpurun brings back at most 64 MiB: turn the reports into text here and drop them
+METRICS=gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active,sm__inst_executed_pipe_tensor.sum,sm__throughput.avg.pct_of_peak_sustained_elapsed,gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed,sm__warps_active.avg.pct_of_peak_sustained_active,launch__registers_per_thread,launch__grid_size,launch__block_size,smsp__issue_active.avg.pct_of_peak_sustained_active,sm__cycles_active.avg,launch__occupancy_limit_shared_mem,launch__shared_mem_per_block_dynamic
+for r in forward_b1 config3_b8 index_7x25 index_7x25_storewarp index_11x41; do
+  [ -f $O/$r.ncu-rep ] || continue
+  ncu -i $O/$r.ncu-rep --page raw --csv --metrics $METRICS > $O/${r}_metrics.csv 2>/dev/null
+  ncu -i $O/$r.ncu-rep --page details > $O/${r}_details.txt 2>/dev/null
+  case $r in index_*) ncu -i $O/$r.ncu-rep --page source --csv > $O/${r}_source.csv 2>/dev/null;; esac
+  rm -f $O/$r.ncu-rep
+done
+gzip -f $O/*_details.txt $O/*_source.csv 2>/dev/null
+cat $O/sanitize_*.log | tail -30
+du -sh $O; ls -la $O
