@@ -107,12 +107,11 @@ __device__ __forceinline__ void tile_load_nbr(const QuerySet& qs, int K, const f
 
 // X[c0 + c][r] = src[(b, cell(r)), c] for c < C (C % 4 == 0), zero for masked / padding rows.
 // cell_of(r) returns the linear row of `src` (>= 0) or -1.
-template <typename CellOf>
+template <int U = 4, typename CellOf>
 __device__ __forceinline__ void gather_features(float* X, int RS, int c0, const float* __restrict__ src, int C,
                                                 int rows, CellOf cell_of)
 {
-    // four tasks per thread and trip: their (L2-latency) loads are in flight together
-    constexpr int U = 4;
+    // U tasks per thread and trip: their (L2-latency) loads are in flight together
     const int c4n = C >> 2, total = rows * c4n;
     for (int t0 = threadIdx.x; t0 < total; t0 += CTA_THREADS * U) {
         float4 v[U];

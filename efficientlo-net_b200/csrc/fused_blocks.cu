@@ -27,7 +27,11 @@ static constexpr int SMEM_LIMIT = 227 * 1024;
 
 // ================================================================================================
 // group_mlp_max
+struct GroupMlpParams;
+__device__ __forceinline__ bool g_direct_gather_dev(const GroupMlpParams& p);
+
 struct GroupMlpParams {
+    int direct_gather;            // tensor-core kernel: gather straight into tensor memory (A/B switch, default on)
     QuerySet qs;
     Window g;
     long long q_base[2], q_end[2];   // global query range of each parameter set
@@ -140,6 +144,7 @@ __global__ void __launch_bounds__(LAUNCH_THREADS, 1) group_mlp_max_kernel(const 
 // ================================================================================================
 // cost volume, stage 1 (point-to-patch)
 struct Cv1Params {
+    int direct_gather;            // tensor-core kernel: gather straight into tensor memory (A/B switch, default on)
     QuerySet qs;
     Window g;
     long long q_first, total_q;      // pixels [q_first, total_q) are this call's queries
@@ -620,6 +625,8 @@ __device__ __forceinline__ float pool_softmax(const float* SL, const float* SV, 
     return pool_softmax_v(SL, [&](int row, int ch) { return SV[row * ld_v + ch]; }, nbr, r0, K, c);
 }
 
+__device__ __forceinline__ bool g_direct_gather_dev(const GroupMlpParams& p) { return p.direct_gather != 0; }
+
 __global__ void __launch_bounds__(TC_LAUNCH_THREADS, 2) group_mlp_max_tc_kernel(const GroupMlpParams p)
 {
     constexpr int RS = TC_ROWS;
@@ -671,6 +678,63 @@ __global__ void __launch_bounds__(TC_LAUNCH_THREADS, 2) group_mlp_max_tc_kernel(
         }
         compute_sync();
     }
+    const int m = pipe.my_row();
+    if (p.nbr_in[set] != nullptr && g_direct_gather_dev(p)) {
+        // Gather straight into tensor memory: a compute thread owns row m of the tile and every other 16-column block
+        // of the A operand, so it can fetch exactly the channels it will write -- the neighbour's xyz and 16-float
+        // pieces of its feature row -- in ONE round trip (all loads issued before any is used), split them and store
+        // them with tcgen05.st.  No staging in shared memory, no transposition, no second trip for the features.
+        int ql, kk;
+        rows.decode(m, ql, kk);
+        int bq = -1;
+        float d0 = 0.f, d1 = 0.f, d2 = 0.f;
+        const float4* frow = nullptr;
+        if (ql >= 0 && ql < p.qt) bq = __float_as_int(ctr[ql * 4 + 3]);
+        if (bq >= 0) {
+            const int cell = nbr[m];
+            float qx = 0.f, qy = 0.f, qz = 0.f;
+            if (cell >= 0) {
+                const float* sx = p.xyz2 + ((size_t)bq * cells2 + cell) * 3;
+                qx = __ldg(sx); qy = __ldg(sx + 1); qz = __ldg(sx + 2);
+                frow = reinterpret_cast<const float4*>(p.feat2[set] + ((size_t)bq * cells2 + cell) * p.Cf);
+            }
+            d0 = qx - ctr[ql * 4 + 0]; d1 = qy - ctr[ql * 4 + 1]; d2 = qz - ctr[ql * 4 + 2];
+        }
+        const int nblk = (cin0 + 15) >> 4, ng = p.Cf >> 2;
+        constexpr int TB = 3;                    // blocks per trip: 15 float4 in flight (Cf = 64: one trip)
+        bool allocated = false;
+        for (int b0 = pipe.my_half(); b0 < nblk || !allocated; b0 += 2 * TB) {
+            // channel c = 16 b + i is feature c - 3: the five float4 groups 4b-1 .. 4b+3 cover a block, shifted by one
+            float4 L[TB][5];
+#pragma unroll
+            for (int u = 0; u < TB; ++u) {
+                const int b = b0 + 2 * u;
+#pragma unroll
+                for (int j = 0; j < 5; ++j) {
+                    const int gi = 4 * b - 1 + j;
+                    L[u][j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (b < nblk && frow != nullptr && gi >= 0 && gi < ng) L[u][j] = __ldg(frow + gi);
+                }
+            }
+            if (!allocated) { pipe.alloc_late(); allocated = true; }   // tensor memory is claimed with the loads in flight
+            const uint32_t addr = pipe.my_lane_addr();                 // (its base address is known only now)
+#pragma unroll
+            for (int u = 0; u < TB; ++u) {
+                const int b = b0 + 2 * u;
+                if (b >= nblk) continue;
+                const float* flat = reinterpret_cast<const float*>(&L[u][0]);
+                uint32_t hi[16], lo[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    float v = flat[i + 1];
+                    if (b == 0 && i < 3) v = i == 0 ? d0 : (i == 1 ? d1 : d2);
+                    tc::split_tf32(v, hi[i], lo[i]);
+                }
+                tc::tmem_st16(addr + b * 16, hi);
+                tc::tmem_st16(addr + TC_A_LO + b * 16, lo);
+            }
+        }
+    } else {
     for (int r = threadIdx.x; r < RS; r += CTA_THREADS) {
         float pc[3], qc[3];
         tc_row_xyz(rows, r, p.qt, nbr, ctr, p.xyz2, cells2, pc, qc);
@@ -686,8 +750,8 @@ __global__ void __launch_bounds__(TC_LAUNCH_THREADS, 2) group_mlp_max_tc_kernel(
     });
     pipe.alloc_late();                           // (a barrier of the compute warps: the gather above is complete)
     pipe.load_a_from_smem(X, 0, cin0, 0);
+    }
     pipe.signal_a_ready();
-    const int m = pipe.my_row();
     float* S = X;                                // staging reused as S[row][cout_last + 1]: X is dead once loaded
     for (int l = 0; l < p.nl; ++l) {
         const bool last = l == p.nl - 1;
@@ -753,6 +817,79 @@ __global__ void __launch_bounds__(TC_LAUNCH_THREADS, 2) cost_volume_1_tc_kernel(
         return;
     }
     pipe.stamp(2);
+    const int m = pipe.my_row();
+    // the 10 xyz channels are needed again by CV_xyz after the tile's A region has been overwritten
+    float x10[16];
+    if (p.direct_gather) {
+        // Gather straight into tensor memory (see group_mlp_max_tc_kernel): row m's [p, q, q - p, |q - p|] from the
+        // centre table and one xyz load, and 16-float pieces of the virtual vector [f1 of the query | f2 of the
+        // neighbour] -- channel c >= 10 is element c - 10 of it, so a 16-channel block is covered by five float4 groups
+        // shifted by two -- all in ONE round trip, then tcgen05.st.
+        int ql, kk;
+        rows.decode(m, ql, kk);
+        const int nq = p.qs.oh * p.qs.ow, ng = C >> 2;
+        const bool okq = ql >= 0 && ql < p.qt && q0 + ql < p.total_q;
+        int bq = -1;
+        if (ql >= 0 && ql < p.qt) bq = __float_as_int(ctr[ql * 4 + 3]);
+        float px = 0.f, py = 0.f, pz = 0.f, qx = 0.f, qy = 0.f, qz = 0.f;
+        const int cell = (ql >= 0 && ql < p.qt) ? nbr[m] : -1;
+        if (bq >= 0) {
+            px = ctr[ql * 4 + 0]; py = ctr[ql * 4 + 1]; pz = ctr[ql * 4 + 2];
+            if (cell >= 0) {
+                const float* sx = p.xyz2 + ((size_t)bq * cells + cell) * 3;
+                qx = __ldg(sx); qy = __ldg(sx + 1); qz = __ldg(sx + 2);
+            }
+        }
+        const float4* f1row = okq ? reinterpret_cast<const float4*>(p.f1 + (size_t)(q0 + ql) * C) : nullptr;
+        const float4* f2row = (ql >= 0 && ql < p.qt && cell >= 0)
+            ? reinterpret_cast<const float4*>(p.f2 + ((size_t)((q0 + ql) / nq) * cells + cell) * C) : nullptr;
+        const int nblk = (xc + 15) >> 4;
+        constexpr int TB = 3;
+        bool allocated = false;
+        for (int b0 = pipe.my_half(); b0 < nblk || !allocated; b0 += 2 * TB) {
+            float4 L[TB][5];
+#pragma unroll
+            for (int u = 0; u < TB; ++u) {
+                const int b = b0 + 2 * u;
+#pragma unroll
+                for (int j = 0; j < 5; ++j) {
+                    const int gi = 4 * b - 3 + j;
+                    L[u][j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (b < nblk && gi >= 0) {
+                        if (gi < ng) { if (f1row != nullptr) L[u][j] = __ldg(f1row + gi); }
+                        else if (gi < 2 * ng) { if (f2row != nullptr) L[u][j] = __ldg(f2row + (gi - ng)); }
+                    }
+                }
+            }
+            if (!allocated) {
+                const float dx = qx - px, dy = qy - py, dz = qz - pz;
+                x10[0] = px; x10[1] = py; x10[2] = pz; x10[3] = qx; x10[4] = qy; x10[5] = qz;
+                x10[6] = dx; x10[7] = dy; x10[8] = dz;
+                x10[9] = sqrtf(__fadd_rn(sumsq_tf(dx, dy, dz), 1e-20f));
+#pragma unroll
+                for (int i = 10; i < 16; ++i) x10[i] = 0.f;
+                pipe.alloc_late();               // tensor memory is claimed with the loads in flight
+                pipe.stamp(3);
+                allocated = true;
+            }
+            const uint32_t addr = pipe.my_lane_addr();
+#pragma unroll
+            for (int u = 0; u < TB; ++u) {
+                const int b = b0 + 2 * u;
+                if (b >= nblk) continue;
+                const float* flat = reinterpret_cast<const float*>(&L[u][0]);
+                uint32_t hi[16], lo[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    float v = flat[i + 2];
+                    if (b == 0 && i < 10) v = x10[i];
+                    tc::split_tf32(v, hi[i], lo[i]);
+                }
+                tc::tmem_st16(addr + b * 16, hi);
+                tc::tmem_st16(addr + TC_A_LO + b * 16, lo);
+            }
+        }
+    } else {
     for (int r = threadIdx.x; r < RS; r += CTA_THREADS) {
         float pc[3], qc[3];
         tc_row_xyz(rows, r, p.qt, nbr, ctr, p.xyz2, cells, pc, qc);
@@ -776,12 +913,10 @@ __global__ void __launch_bounds__(TC_LAUNCH_THREADS, 2) cost_volume_1_tc_kernel(
     }
     pipe.alloc_late();                          // (a barrier of the compute warps: the gather above is complete)
     pipe.stamp(3);
-    const int m = pipe.my_row();
-    // the 10 xyz channels are needed again by CV_xyz after the tile's A region has been overwritten
-    float x10[16];
 #pragma unroll
     for (int i = 0; i < 16; ++i) x10[i] = i < 10 ? X[act_index(i, m, RS)] : 0.f;
     pipe.load_a_from_smem(X, 0, xc, 0);
+    }
     pipe.signal_a_ready();
     pipe.stamp(4);
     // pool staging (the X region is dead once every thread has loaded its row): F and logits as [row][65]
@@ -877,7 +1012,7 @@ __global__ void __launch_bounds__(TC_LAUNCH_THREADS, 2) cost_volume_2_tc_kernel(
             rows.decode(r, ql, k);
             return (ql >= 0 && ql < qt && q0 + ql < total) ? q0 + ql : -1;
         });
-        gather_features(X, RS, 16 + C, p.cv1, 64, RS, [&](int r) -> long long {
+        gather_features<8>(X, RS, 16 + C, p.cv1, 64, RS, [&](int r) -> long long {
             int ql, k;
             rows.decode(r, ql, k);
             if (ql < 0 || ql >= qt || nbr[r] < 0) return -1;
@@ -921,7 +1056,7 @@ __global__ void __launch_bounds__(TC_LAUNCH_THREADS, 2) cost_volume_2_tc_kernel(
         }
 }
 
-__global__ void __launch_bounds__(TC_LAUNCH_THREADS, 1) row_mlp_tc_kernel(const RowMlpParams p)
+__global__ void __launch_bounds__(TC_LAUNCH_THREADS, 2) row_mlp_tc_kernel(const RowMlpParams p)
 {
     constexpr int RS = TC_ROWS;
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -956,7 +1091,8 @@ __global__ void __launch_bounds__(TC_LAUNCH_THREADS, 1) row_mlp_tc_kernel(const 
         for (int i = 0; i < p.nsrc[ph]; ++i) {
             if (p.src_prev[ph][i] || !p.stage_here[ph][i]) continue;    // a source used twice is staged once
             {
-                gather_features(X, RS, p.slot[ph][i], p.src[set][ph][i], p.src_c[ph][i], RS, [&](int r) -> long long {
+                // 64 channels x 128 rows are 8 float4 per thread: one round trip per source instead of two
+                gather_features<8>(X, RS, p.slot[ph][i], p.src[set][ph][i], p.src_c[ph][i], RS, [&](int r) -> long long {
                     return (r < rt && r0 + r < rows) ? r0 + r : -1;
                 });
             }
@@ -1222,6 +1358,8 @@ extern "C" int elo_group_mlp_max(const elo_group_mlp_desc* d, void* stream)
     if (d->batch_size == 0) return ELO_OK;
 
     GroupMlpParams p;
+    static const int direct_gather = getenv("ELO_DIRECT_GATHER") ? atoi(getenv("ELO_DIRECT_GATHER")) : 1;
+    p.direct_gather = direct_gather;
     p.qs = make_queries(&d->queries);
     p.g = make_window(&d->window[0]);
     long long per_set = (long long)d->batch_size * p.qs.oh * p.qs.ow;
@@ -1299,6 +1437,8 @@ extern "C" int elo_cost_volume_1(const elo_cost_volume_desc* d, void* stream)
     if (d->window_q.K > 64) return set_error(ELO_ERR_UNSUPPORTED, "cost_volume_1: nsample_q > 64");
     if (d->batch_size == 0) return ELO_OK;
     Cv1Params p;
+    static const int direct_gather = getenv("ELO_DIRECT_GATHER") ? atoi(getenv("ELO_DIRECT_GATHER")) : 1;
+    p.direct_gather = direct_gather;
     p.sl_in_ring = 0;
     p.qs.H1 = d->H; p.qs.W1 = d->W; p.qs.oh = d->H; p.qs.ow = d->W; p.qs.qs_h = 1; p.qs.qs_w = 1;
     p.g = make_window(&d->window_q);
@@ -1497,9 +1637,13 @@ extern "C" int elo_row_mlp(const elo_row_mlp_desc* d, void* stream)
         p.total_chunks = chunks_t;
         p.stage_ch = stage_ch;
         const size_t base = tc_base_smem(0, (size_t)stage_ch * TC_ROWS);
-        p.nring = tc_pick_ring(base, chunks_t);
+        // two tiles per SM where the staged sources leave room for a two-slot weight ring in half an SM's shared
+        // memory (level 0: 144 staged channels): one tile's gather and stores then overlap the other's MMA chain
+        static const bool two_ok = !(getenv("ELO_ROWMLP_TWO") && atoi(getenv("ELO_ROWMLP_TWO")) == 0);
+        const bool two = two_ok && base + 2 * (size_t)TC_CHUNK_BYTES <= (size_t)SMEM_HALF;
+        p.nring = tc_pick_ring(base, chunks_t, two);
         if (p.nring < 2) return set_error(ELO_ERR_UNSUPPORTED, "row_mlp: tile does not fit shared memory");
-        const TcChoice tc = choose_tc_tile(p.rows, 1, d->nsets);
+        const TcChoice tc = choose_tc_tile(p.rows, 1, d->nsets, two ? 2 : 1);
         p.rt = tc.per_tile;
         return launch_tc(row_mlp_tc_kernel, p, dim3(tc.tiles, d->nsets), base + (size_t)p.nring * TC_CHUNK_BYTES,
                          (cudaStream_t)stream, "row_mlp (tensor core) launch");
