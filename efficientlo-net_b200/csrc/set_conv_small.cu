@@ -8,6 +8,7 @@
 // (weights are warp-uniform float4 broadcasts from shared memory) and the max over the K neighbours is
 // a shuffle butterfly.  Nothing but the (B, n, C_out) result is written.
 #include <cuda_runtime.h>
+#include <stdlib.h>
 
 #include "../../include/elo_b200.h"
 #include "elo_common.cuh"
@@ -190,7 +191,8 @@ static int launch_small(const SmallParams& p, int nsets, cudaStream_t st)
     long long wpc = (groups * nsets + 2 * sms - 1) / (2 * sms);
     wpc = wpc < 4 ? 4 : (wpc > 8 ? 8 : wpc);      // at least 4 warps share a CTA's weight load
     long long ctas = (groups + wpc - 1) / wpc;
-    const long long cap = sms * 4 / nsets;
+    static const int cap_per_sm = getenv("ELO_SETCONV_CAP") ? atoi(getenv("ELO_SETCONV_CAP")) : 4;
+    const long long cap = sms * cap_per_sm / nsets;
     if (ctas > cap) ctas = cap;
     auto kern = set_conv_small_kernel<CF, C1, C2, C3, K>;
     if (smem > 48 * 1024) {
