@@ -75,6 +75,10 @@ def _window(kernel_size, K, distance, stride_h, stride_w, small_h, small_w, rand
     return w
 
 
+import os as _os
+_SMALL_ONLY = _os.environ.get("ELO_SETCONV_SMALL_ONLY", "0") == "1"      # A/B: keep narrow chains on set_conv_small
+
+
 def _is_training(is_training):
     return is_training is True or (isinstance(is_training, torch.Tensor) and bool(is_training))
 
@@ -170,10 +174,18 @@ def set_conv(xyz_proj, points_proj, sel, K_sample, kernel_size, distance, layer_
     for i, wd in enumerate(widths):
         d.cout[i] = wd
     d.xyz1 = d.xyz2 = xyz_proj.data_ptr()
-    big = all(wd in (64, 128) for wd in widths)
+    # the GEMM engines take 64- / 128-wide layers.  A chain that ENDS that wide but has narrower hidden layers (pyramid
+    # layer 2: 35 -> 32 -> 32 -> 64) runs there too, its hidden layers widened with zero columns: 57 tensor-core tiles
+    # instead of 58 CTAs that each push 4192 serial FMAs per row through registers (34 -> 13 us at B = 1).
+    native = all(wd in (64, 128) for wd in widths)
+    big = native or (widths[-1] in (64, 128) and C % 4 == 0 and all(wd <= 64 for wd in widths[:-1]) and not _SMALL_ONLY)
+    pad = 64 if big and not native else None
+    if pad:
+        for i in range(len(widths) - 1):
+            d.cout[i] = max(widths[i], pad) if widths[i] not in (64, 128) else widths[i]
     if big and points_proj is None:
         points_proj = torch.zeros((Bt, H, W, C), dtype=torch.float32, device=dev)
-    weights = store.stream(layer_scopes) if big else store.plain(layer_scopes)
+    weights = store.stream(layer_scopes, pad_hidden=pad) if big else store.plain(layer_scopes)
     for s in range(2):
         d.feat2[s] = _lib.ptr(points_proj)
         d.weights[s] = weights.data_ptr()

@@ -39,14 +39,15 @@ class ParamStore:
         # different stream sets its own (engine.PWCLOEngine does) so that their forwards do not share them
         self.scratch_ns = 0
 
-    def stream(self, scopes):
-        """Packed weights of a layer chain in the format of the MLP engine currently selected."""
+    def stream(self, scopes, pad_hidden=None):
+        """Packed weights of a layer chain in the format of the MLP engine currently selected (pad_hidden: see
+        packing.folded_chain)."""
         from . import _lib
         tc = _lib.mlp_engine() == 1
-        key = ("stream_tc" if tc else "stream",) + tuple(scopes)
+        key = ("stream_tc" if tc else "stream", pad_hidden) + tuple(scopes)
         if key not in self._cache:
             pack = packing.pack_stream_tc if tc else packing.pack_stream
-            self._cache[key] = pack(self.P, scopes).to(self.device)
+            self._cache[key] = pack(self.P, scopes, pad_hidden).to(self.device)
         return self._cache[key]
 
     def plain(self, scopes):
