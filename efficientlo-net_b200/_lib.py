@@ -188,6 +188,14 @@ def set_store_warp_min_cells(min_cells):
     check(h.elo_set_store_warp_min_cells(int(min_cells)), "elo_set_store_warp_min_cells")
 
 
+def set_tile_staging(mode):
+    """Tile staging of the tiled index kernel: 0 bulk copies (TMA engine), 1 plain loads."""
+    h = lib()
+    h.elo_set_tile_staging.argtypes = [_c_int]
+    h.elo_set_tile_staging.restype = _c_int
+    check(h.elo_set_tile_staging(int(mode)), "elo_set_tile_staging")
+
+
 def set_tile_policy(policy):
     """0: latency (spread small calls over all SMs), 1: throughput (full 128-row tiles)."""
     check(lib().elo_set_tile_policy(int(policy)), "elo_set_tile_policy")

@@ -22,6 +22,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "elo_bulk.cuh"
+
 namespace elo {
 
 constexpr int CTA_THREADS = 256;                   // compute threads (8 warps)
@@ -36,50 +38,6 @@ constexpr int MAX_RING = 8;                        // chunks in flight (host pic
 __device__ __forceinline__ int act_index(int c, int r, int RS)
 {
     return c * RS + ((((r >> 2) ^ ((c >> 2) & 7))) << 2) + (r & 3);
-}
-
-// ---- mbarrier / bulk-copy primitives (PTX) -------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p)
-{
-    return (uint32_t)__cvta_generic_to_shared(p);
-}
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count)
-{
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_fence_init()
-{
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes)
-{
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
-                 : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
-{
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "WAIT_%=:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra DONE_%=;\n\t"
-        "bra WAIT_%=;\n\t"
-        "DONE_%=:\n\t}" ::"r"(smem_u32(bar)),
-        "r"(parity)
-        : "memory");
-}
-// global -> shared bulk copy through the TMA engine; completes `bytes` on the mbarrier
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar)
-{
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                     smem_u32(dst)),
-                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
-}
-
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar)
-{
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
 // barrier over the 256 compute threads only (the producer warp never joins it)

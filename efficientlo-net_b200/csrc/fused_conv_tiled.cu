@@ -36,6 +36,7 @@
 #include <vector>
 
 #include "../../include/elo_b200.h"
+#include "elo_bulk.cuh"
 #include "elo_common.cuh"
 #include "elo_count_rows.cuh"
 #include "elo_search.cuh"
@@ -74,6 +75,7 @@ struct TiledParams {
     int dbg;             // timing aid (ELO_TILED_DBG): 1 = query warps skip the walk, 2 = store warp skips its rows
     int pitch;           // row pitch of the staged tile in cells (TQ + kW)
     float near_bound;    // sqrt(distance^2 / 12.5): coordinates within it are all mutually in range
+    int bulk;            // 1: the tile's rows come in by bulk copies (xyz2 is 16-byte aligned); 0: plain loads
     int walk[MAX_WALK];  // select-K: window cells centre-out, (dh << 16) | (dw & 0xffff)
     int walk_to[MAX_WALK];  // ... and their byte offsets in the staged tile, (row * pitch + col) * 16
 };
@@ -158,6 +160,7 @@ fused_conv_tiled_kernel(const __grid_constant__ TiledParams p)
     int* s_vsum = reinterpret_cast<int*>(take((size_t)(p.pitch + 1) * 4));   // store warp: prefix of the column sums
     int* s_misc = reinterpret_cast<int*>(take(64));                          // tie count, reference column, geometry
     unsigned char* tile = take((size_t)p.tile_bytes);                        // float4 per cell; replay scratch later
+    uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_misc + 14);              // mbarrier of the tile's bulk copies
 
     // ---- this thread's query -----------------------------------------------------------------------
     const long long q0 = (long long)blockIdx.x * TQ;
@@ -235,6 +238,8 @@ fused_conv_tiled_kernel(const __grid_constant__ TiledParams p)
                 tg.staged = -1;
             }
             *reinterpret_cast<TileGeom*>(s_misc + 4) = tg;
+            mbar_init(s_bar, 32);            // the 32 lanes of warp 0 each announce the bytes of their tile rows
+            mbar_fence_init();
         }
         __syncthreads();
     }
@@ -261,54 +266,140 @@ fused_conv_tiled_kernel(const __grid_constant__ TiledParams p)
         // is, every point of the neighbourhood is within `distance` of every centre (|c - q|^2 <= 12 bound^2),
         // so valid_in_dis_idx == valid_idx and the walk needs neither the range test nor its counter.
         bool far = cvalid && !(fmaxf(fmaxf(fabsf(xc), fabsf(yc)), fabsf(zc)) <= p.near_bound);
+        // ---- walk tables, and where each query's window starts in the tile (for the store warp) -----------------
+        bool tables_done = false;
+        auto fill_tables = [&]() {
+            if (SELECT && !store_warp)
+                s_qpos[tid] = (staged && cvalid) ? (((ch - tg.hmin) << 16) | (rel - tg.rmin)) : -1;
+            for (int j = tid; j < kt; j += NT) {
+                int pk, to;
+                if (SELECT) {
+                    pk = p.walk[j]; to = p.walk_to[j];
+                } else {
+                    const int pp = __ldg(p.random_hw + j);
+                    const int r = pp / g.kW, cc = pp - r * g.kW;
+                    pk = ((r - hh2) << 16) | ((cc - hw2) & 0xffff);
+                    to = (r * pitch + cc) * 16;
+                }
+                walk_pk[j] = pk;
+                walk_to[j] = to;
+            }
+            tables_done = true;
+        };
         if (staged) {
             const float* g2 = p.xyz2 + (size_t)tg.b * g.h2 * g.w2 * 3;
             float4* t4 = reinterpret_cast<float4*>(tile);
             int c0 = tg.col0 % g.w2;
             if (c0 < 0) c0 += g.w2;
-            // a column of the tile per thread; its rows in groups of SR whose loads are all issued before any of
-            // them is used (a plain row loop would pay one L2 round trip per row)
             constexpr int SR = 8;
-            for (int c = tid; c < tg.tw; c += NT) {
-                const int gc = (c0 + c) % g.w2;
-                for (int r0 = 0; r0 < tg.th; r0 += SR) {
-                    float x[SR], y[SR], z[SR];
-#pragma unroll
-                    for (int i = 0; i < SR; ++i) {
-                        const int gr = tg.row0 + r0 + i;
-                        x[i] = y[i] = z[i] = 0.f;
-                        if (r0 + i < tg.th && gr >= 0 && gr < g.h2) {
-                            const float* s = g2 + ((size_t)gr * g.w2 + gc) * 3;
-                            x[i] = __ldg(s); y[i] = __ldg(s + 1); z[i] = __ldg(s + 2);
-                        }
+            // empty pixel (reference :98-104); FSETP.GTU there: a NaN pixel counts as a point
+            auto put = [&](int r, int c, float x, float y, float z) {
+                t4[r * pitch + c] = make_float4(x, y, z, sq3(x, y, z) <= 1e-10f ? 1.0f : 0.0f);
+                far = far || !(fmaxf(fmaxf(fabsf(x), fabsf(y)), fabsf(z)) <= p.near_bound);
+            };
+            if (p.bulk && tg.tw <= g.w2) {
+                // ---- bulk-copy staging (TMA engine, UBLKCP): a tile row is one contiguous run of the grid, or two
+                // when it wraps around the cylinder.  The runs land PACKED (12 bytes per point) at the head of the
+                // row's own slot of the float4 tile -- start rounded down and length rounded up to four points, so
+                // source, destination and size are multiples of 16 bytes -- and are then spread in place to
+                // (x, y, z, empty) float4s, highest columns first so that no packed point is overwritten before it
+                // has been read.  Rows outside the image take no copy; the last row of the tensor (whose rounded-up
+                // run could end past the allocation) keeps plain loads.
+                const int nA = min(tg.tw, g.w2 - c0);                 // cells before the wrap
+                const long long rowcell0 = (long long)tg.b * g.h2 * g.w2;
+                auto row_mode = [&](int gr) {                         // 0 outside the image, 1 bulk copy, 2 plain loads
+                    return (gr < 0 || gr >= g.h2) ? 0 : (tg.b == p.B - 1 && gr == g.h2 - 1) ? 2 : 1;
+                };
+                // a run of n cells whose first cell has index = lead (mod 4) in the tensor: bytes of the copy
+                auto run_bytes = [](int lead, int n) { return ((lead + n + 3) & ~3) * 12; };
+                const int rc0m = (int)(rowcell0 & 3), w2m = g.w2 & 3;
+                // la / lb: cells between the rounded-down start of the first / second run of grid row gr and its data
+                auto leads = [&](int gr, int& la, int& lb) { lb = (rc0m + gr * w2m) & 3; la = (lb + c0) & 3; };
+                if (warp == 0) {
+                    unsigned bytes = 0;
+                    for (int r = lane; r < tg.th; r += 32) {
+                        const int gr = tg.row0 + r;
+                        if (row_mode(gr) != 1) continue;
+                        int la, lb;
+                        leads(gr, la, lb);
+                        bytes += run_bytes(la, nA) + (nA < tg.tw ? run_bytes(lb, tg.tw - nA) : 0);
                     }
+                    if (bytes) mbar_expect_tx(s_bar, bytes); else mbar_arrive(s_bar);
+                    for (int r = lane; r < tg.th; r += 32) {
+                        const int gr = tg.row0 + r;
+                        if (row_mode(gr) != 1) continue;
+                        int la, lb;
+                        leads(gr, la, lb);
+                        const long long ra = rowcell0 + (long long)gr * g.w2;
+                        unsigned char* slot = tile + (size_t)r * pitch * 16;
+                        const int ba = run_bytes(la, nA);
+                        bulk_g2s(slot, p.xyz2 + (ra + c0 - la) * 3, ba, s_bar);
+                        if (nA < tg.tw) bulk_g2s(slot + ba, p.xyz2 + (ra - lb) * 3, run_bytes(lb, tg.tw - nA), s_bar);
+                    }
+                }
+                fill_tables();               // under the copies' latency
+                mbar_wait(s_bar, 0);
+                // a packed point of column c sits below byte 12 (c + 9) of its slot and the float4 of column c' at
+                // byte 16 c': columns >= c_lo may be written while columns < c_lo are still packed iff c_lo >= 27
+                for (int r0 = 0; r0 < tg.th; r0 += SR) {
+                    for (int c_hi = tg.tw; c_hi > 0;) {
+                        int c_lo = c_hi - NT;
+                        if (c_lo < 27) c_lo = c_hi <= NT ? 0 : 27;
+                        const int c = c_lo + tid;
+                        const bool mine = c < c_hi;
+                        float x[SR], y[SR], z[SR];
 #pragma unroll
-                    for (int i = 0; i < SR; ++i) {
-                        if (r0 + i >= tg.th) continue;
-                        // empty pixel (reference :98-104); FSETP.GTU there: a NaN pixel counts as a point
-                        t4[(r0 + i) * pitch + c] = make_float4(x[i], y[i], z[i], sq3(x[i], y[i], z[i]) <= 1e-10f ? 1.0f : 0.0f);
-                        far = far || !(fmaxf(fmaxf(fabsf(x[i]), fabsf(y[i])), fabsf(z[i])) <= p.near_bound);
+                        for (int i = 0; i < SR; ++i) {
+                            x[i] = y[i] = z[i] = 0.f;
+                            const int r = r0 + i, gr = tg.row0 + r;
+                            if (!mine || r >= tg.th) continue;
+                            const int mode = row_mode(gr);
+                            if (mode == 1) {
+                                int la, lb;
+                                leads(gr, la, lb);
+                                const float* s = reinterpret_cast<const float*>(tile + (size_t)r * pitch * 16 +
+                                                                                (c < nA ? 0 : run_bytes(la, nA))) +
+                                                 (c < nA ? la + c : lb + c - nA) * 3;
+                                x[i] = s[0]; y[i] = s[1]; z[i] = s[2];
+                            } else if (mode == 2) {
+                                const float* s = g2 + ((size_t)gr * g.w2 + (c0 + c) % g.w2) * 3;
+                                x[i] = __ldg(s); y[i] = __ldg(s + 1); z[i] = __ldg(s + 2);
+                            }
+                        }
+                        __syncthreads();
+                        if (mine) {
+#pragma unroll
+                            for (int i = 0; i < SR; ++i)
+                                if (r0 + i < tg.th) put(r0 + i, c, x[i], y[i], z[i]);
+                        }
+                        c_hi = c_lo;
+                    }
+                }
+            } else {
+                // a column of the tile per thread; its rows in groups of SR whose loads are all issued before any
+                // of them is used (a plain row loop would pay one L2 round trip per row)
+                for (int c = tid; c < tg.tw; c += NT) {
+                    const int gc = (c0 + c) % g.w2;
+                    for (int r0 = 0; r0 < tg.th; r0 += SR) {
+                        float x[SR], y[SR], z[SR];
+#pragma unroll
+                        for (int i = 0; i < SR; ++i) {
+                            const int gr = tg.row0 + r0 + i;
+                            x[i] = y[i] = z[i] = 0.f;
+                            if (r0 + i < tg.th && gr >= 0 && gr < g.h2) {
+                                const float* s = g2 + ((size_t)gr * g.w2 + gc) * 3;
+                                x[i] = __ldg(s); y[i] = __ldg(s + 1); z[i] = __ldg(s + 2);
+                            }
+                        }
+#pragma unroll
+                        for (int i = 0; i < SR; ++i)
+                            if (r0 + i < tg.th) put(r0 + i, c, x[i], y[i], z[i]);
                     }
                 }
             }
         }
         if (far) s_misc[2] = 1;          // some coordinate of the neighbourhood is large, infinite or NaN
-        if (SELECT && !store_warp)       // where this query's window starts in the tile (for the store warp)
-            s_qpos[tid] = (staged && cvalid) ? (((ch - tg.hmin) << 16) | (rel - tg.rmin)) : -1;
-        // ---- walk tables ----------------------------------------------------------------------------------
-        for (int j = tid; j < kt; j += NT) {
-            int pk, to;
-            if (SELECT) {
-                pk = p.walk[j]; to = p.walk_to[j];
-            } else {
-                const int pp = __ldg(p.random_hw + j);
-                const int r = pp / g.kW, cc = pp - r * g.kW;
-                pk = ((r - hh2) << 16) | ((cc - hw2) & 0xffff);
-                to = (r * pitch + cc) * 16;
-            }
-            walk_pk[j] = pk;
-            walk_to[j] = to;
-        }
+        if (!tables_done) fill_tables();
         __syncthreads();
         const bool all_near = SELECT && staged && s_misc[2] == 0;
         early_rows = SW && all_near && count_rows;
@@ -680,6 +771,8 @@ fused_conv_tiled_kernel(const __grid_constant__ TiledParams p)
 
 static std::atomic<int> g_index_kernel{0};   // 0: by query count, 1: always tiled, 2: always warp-per-query
 static std::atomic<int> g_store_warp_min_kt{getenv("ELO_STORE_WARP_KT") ? atoi(getenv("ELO_STORE_WARP_KT")) : 256};
+// how the tile comes into shared memory: 0 = bulk copies (TMA engine), 1 = plain loads (elo_set_tile_staging)
+static std::atomic<int> g_tile_staging{getenv("ELO_TILE_STAGING") ? atoi(getenv("ELO_TILE_STAGING")) : 0};
 
 static unsigned magic_of(unsigned d)
 {
@@ -736,6 +829,8 @@ static void tiled_prepare(TiledParams& p, bool select)
     p.magic_kt = magic_of((unsigned)g.kt);
     p.magic_k = magic_of((unsigned)g.K);
     p.dbg = getenv("ELO_TILED_DBG") ? atoi(getenv("ELO_TILED_DBG")) : 0;
+    p.bulk = (g_tile_staging.load(std::memory_order_relaxed) == 0 && p.xyz2 != nullptr &&
+              (reinterpret_cast<uintptr_t>(p.xyz2) & 15) == 0) ? 1 : 0;
     if (select) {
         // centre-out walk: nearest pixels first, rows weighted 2x (a LiDAR's rows are ~2x further apart than
         // its columns), so the K-th key tightens early and few later cells pass the filter
@@ -870,3 +965,12 @@ extern "C" int elo_set_store_warp_min_cells(int min_cells)
 }
 
 extern "C" int elo_get_store_warp_min_cells(void) { return elo::g_store_warp_min_kt.load(std::memory_order_relaxed); }
+
+extern "C" int elo_set_tile_staging(int mode)
+{
+    if (mode < 0 || mode > 1) return elo::set_error(ELO_ERR_INVALID_ARGUMENT, "elo_set_tile_staging: 0 or 1");
+    elo::g_tile_staging.store(mode, std::memory_order_relaxed);
+    return ELO_OK;
+}
+
+extern "C" int elo_get_tile_staging(void) { return elo::g_tile_staging.load(std::memory_order_relaxed); }

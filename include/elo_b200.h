@@ -95,6 +95,13 @@ int elo_set_index_kernel(int which);
  * never.  Results are identical either way. */
 int elo_set_store_warp_min_cells(int min_cells);
 int elo_get_store_warp_min_cells(void);
+/* How the tile-staged index kernel brings a CTA's neighbourhood of the xyz2 grid into shared memory:
+ *   0 (default)  bulk copies through the TMA engine (cp.async.bulk, one or two per tile row), spread in place to the
+ *                padded (x, y, z, empty) float4 grid; needs xyz2 on a 16-byte boundary, else falls back to 1;
+ *   1            plain loads by the CTA's threads.
+ * Results are identical either way. */
+int elo_set_tile_staging(int mode);
+int elo_get_tile_staging(void);
 int elo_get_index_kernel(void);
 /* Programmatic dependent launch between the kernels of this library (default on; environment ELO_PDL=0
  * turns it off): a kernel's prologue -- barrier / tensor-memory set-up, weight prefetch -- overlaps the

@@ -13,16 +13,19 @@ pytestmark = pytest.mark.gpu
 GOLDEN = os.path.join(os.path.dirname(__file__), "golden", "index_golden.npz")
 
 
-@pytest.fixture(autouse=True, params=["tiled", "tiled+storewarp", "warp"])
+@pytest.fixture(autouse=True, params=["tiled", "tiled+storewarp", "tiled+plainloads", "warp"])
 def index_kernel(request, elo):
     """Every test of this module runs on all work decompositions of the index ops: the tile-staged
     thread-per-query kernel (fused_conv_tiled.cu) without and with its store warp (select-K: one more warp per CTA
-    writes the count rows while the query warps walk), and one warp per query (fused_conv_index.cu)."""
+    writes the count rows while the query warps walk), with its tile staged by bulk copies (default) or by plain loads,
+    and one warp per query (fused_conv_index.cu)."""
     elo._lib.set_index_kernel(2 if request.param == "warp" else 1)
     elo._lib.set_store_warp_min_cells(0 if request.param == "tiled+storewarp" else 1 << 30)
+    elo._lib.set_tile_staging(1 if request.param == "tiled+plainloads" else 0)
     yield request.param
     elo._lib.set_index_kernel(0)
     elo._lib.set_store_warp_min_cells(256)
+    elo._lib.set_tile_staging(0)
 
 
 def run_cuda(elo, cuda, mode, xyz1, xyz2, idx_n2, random_hw, H, W, npoints, kH, kW, K, flag_copy,
@@ -169,6 +172,24 @@ def test_unaligned_output_buffers(elo, cuda, mode):
     cases.assert_same(tuple(g.cpu().numpy() for g in got), want, "unaligned " + mode)
     for b in bufs.values():                            # guard elements untouched
         assert (b[:pad] == -7).all() and (b[-5:] == -7).all()
+
+
+@pytest.mark.parametrize("mode", ["select", "random"])
+def test_unaligned_input_grid(elo, cuda, mode):
+    """xyz2 that is only 4-byte aligned (a view one float into a buffer): bulk copies need 16-byte aligned sources, so the
+    tiled kernel stages its tile with plain loads; same outputs."""
+    rng = np.random.default_rng(22)
+    case = raster_case(rng, mode, 2, 6, 50, 5, 9, 8, 1, 1, 3.0, flag_copy=1)
+    want = cases.call(io.port, case, nthreads=8)
+    t = {k: torch.as_tensor(case[k]).to(cuda) for k in ("xyz1", "idx_n2", "random_hw")}
+    buf = torch.zeros(case["xyz2"].size + 4, device=cuda)
+    buf[1:1 + case["xyz2"].size] = torch.as_tensor(case["xyz2"]).to(cuda).reshape(-1)
+    xyz2 = buf[1:1 + case["xyz2"].size].reshape(case["xyz2"].shape)
+    assert xyz2.data_ptr() % 16 == 4
+    fn = elo.fused_conv_select_k if mode == "select" else elo.fused_conv_random_k
+    outs = fn(t["xyz1"], xyz2, t["idx_n2"], t["random_hw"], 6, 50, case["npoints"], 5, 9, 8, 1, 3.0, 1, 1)
+    torch.cuda.synchronize()
+    cases.assert_same(tuple(o.cpu().numpy() for o in outs), want, "unaligned xyz2 " + mode)
 
 
 @pytest.mark.parametrize("kH,kW", [(31, 33), (33, 33)])
