@@ -50,50 +50,58 @@ __device__ __forceinline__ void write_count_rows(float* o_valid, float* o_vdis, 
         // warp-uniform shortcut: no lane of the chunk straddles two rows (one term per element instead of two)
         const bool straddle = __any_sync(FULL_MASK, on && r0 != r3);
         if (!on) continue;
-        // element i sits in row r0 at pos0 + i while that is < kt, else in row r3 at pos0 + i - kt
-        float pa[4], pb[4];
+        // element i sits in row r0 at pos0 + i while that is < kt, else in row r3 at pos0 + i - kt: its count is read
+        // from row r0 + sh[i] of the block and its position is pe[i] -- one shared-memory load and one FADD.SAT per
+        // element when a lane of the chunk straddles two rows, one load per float4 when none does
+        float pe[4];
+        int sh[4];                                  // row of element i relative to r0 (0 or r3 - r0)
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             const bool lo = (int)pos0 + i < kt;
-            pa[i] = lo ? (float)((int)pos0 + i) : 1e9f;
-            pb[i] = lo ? 1e9f : (float)((int)pos0 + i - kt);
+            pe[i] = (float)(lo ? (int)pos0 + i : (int)pos0 + i - kt);
+            sh[i] = lo ? 0 : r3 - r0;
         }
-        float4* ov = o_valid ? reinterpret_cast<float4*>(o_valid) + f : nullptr;
-        float4* od = o_vdis ? reinterpret_cast<float4*>(o_vdis) + f : nullptr;
-        const float* nva = nv + r0; const float* nvb = nv + r3;
-        const float* nsa = ns + r0; const float* nsb = ns + r3;
-        auto body = [&](auto STR, auto SAME) {
-            constexpr bool two = decltype(STR)::value, one_array = decltype(SAME)::value;
+        // the block of four rows advances every pointer by kt float4s = 16 kt bytes: a warp-uniform byte offset
+        // added to the lane's fixed column address
+        char* const ovb = reinterpret_cast<char*>(o_valid) + (size_t)f * 16;
+        char* const odb = reinterpret_cast<char*>(o_vdis) + (size_t)f * 16;
+        const unsigned step = (unsigned)kt * 16u;
+        const float* nva = nv + r0;
+        const float* nsa = ns + r0;
+        auto body = [&](auto STR, auto SAME, auto BOTH) {
+            constexpr bool two = decltype(STR)::value, one_array = decltype(SAME)::value, both = decltype(BOTH)::value;
 #pragma unroll 8
             for (int blk = 0; blk < nblk; ++blk) {
                 float a4[4], d4[4];
-                const float va = nva[4 * blk];
-#pragma unroll
-                for (int i = 0; i < 4; ++i) a4[i] = __saturatef(va - pa[i]);
                 if constexpr (two) {
-                    const float vb = nvb[4 * blk];
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) a4[i] += __saturatef(vb - pb[i]);
+                    for (int i = 0; i < 4; ++i) a4[i] = __saturatef(nva[4 * blk + sh[i]] - pe[i]);
+                } else {
+                    const float va = nva[4 * blk];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) a4[i] = __saturatef(va - pe[i]);
                 }
                 if constexpr (one_array) {
 #pragma unroll
                     for (int i = 0; i < 4; ++i) d4[i] = a4[i];
+                } else if constexpr (two) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) d4[i] = __saturatef(nsa[4 * blk + sh[i]] - pe[i]);
                 } else {
                     const float da = nsa[4 * blk];
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) d4[i] = __saturatef(da - pa[i]);
-                    if constexpr (two) {
-                        const float db = nsb[4 * blk];
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) d4[i] += __saturatef(db - pb[i]);
-                    }
+                    for (int i = 0; i < 4; ++i) d4[i] = __saturatef(da - pe[i]);
                 }
-                if (ov) __stcs(ov + (size_t)blk * kt, make_float4(a4[0], a4[1], a4[2], a4[3]));
-                if (od) __stcs(od + (size_t)blk * kt, make_float4(d4[0], d4[1], d4[2], d4[3]));
+                const unsigned off = (unsigned)blk * step;
+                if (both || o_valid) __stcs(reinterpret_cast<float4*>(ovb + off), make_float4(a4[0], a4[1], a4[2], a4[3]));
+                if (both || o_vdis) __stcs(reinterpret_cast<float4*>(odb + off), make_float4(d4[0], d4[1], d4[2], d4[3]));
             }
         };
-        if (straddle) { if (same) body(std::true_type{}, std::true_type{}); else body(std::true_type{}, std::false_type{}); }
-        else          { if (same) body(std::false_type{}, std::true_type{}); else body(std::false_type{}, std::false_type{}); }
+        auto pick = [&](auto STR, auto SAME) {
+            if (o_valid && o_vdis) body(STR, SAME, std::true_type{}); else body(STR, SAME, std::false_type{});
+        };
+        if (straddle) { if (same) pick(std::true_type{}, std::true_type{}); else pick(std::true_type{}, std::false_type{}); }
+        else          { if (same) pick(std::false_type{}, std::true_type{}); else pick(std::false_type{}, std::false_type{}); }
     }
     // rows that do not fill a block of four (or unaligned outputs): element by element
     const unsigned nel = (unsigned)nrows * kt;

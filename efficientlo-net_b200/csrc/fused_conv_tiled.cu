@@ -49,7 +49,20 @@ namespace elo {
 constexpr int QG = 16;       // window cells between two drains of the candidate queue
 constexpr int LB = 8;        // staged cells loaded ahead of their use
 constexpr int MAX_WALK = 1024;               // window cells whose host-sorted walk fits the kernel parameters
+#ifdef ELO_TILED_TS      // experiment build only (tools/tiled_timeline.py): per-CTA phase timestamps
+__device__ unsigned long long g_tiled_ts[1024 * 8];
+__device__ __forceinline__ unsigned long long tiled_now()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+#define TILED_TS(k, who) do { if (threadIdx.x == (who) && blockIdx.x < 1024) g_tiled_ts[blockIdx.x * 8 + (k)] = tiled_now(); } while (0)
+#else
+#define TILED_TS(k, who) do { } while (0)
+#endif
 constexpr unsigned KEY_NONE = 0x7f000000u;   // larger than any accepted key (d <= distance^2 < 1e10)
+constexpr float EMPTY_X = 2e19f;             // x of an empty pixel in the staged tile: (x - EMPTY_X)^2 = +inf for |x| < 1e19
 
 struct TiledParams {
     int B, H, W, N;
@@ -138,6 +151,7 @@ fused_conv_tiled_kernel(const __grid_constant__ TiledParams p)
     extern __shared__ __align__(16) unsigned char smem_raw[];
     pdl_trigger();
     pdl_wait();
+    TILED_TS(0, 0);
     const Window& g = p.g;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int kt = g.kt, K = g.K;
@@ -243,6 +257,7 @@ fused_conv_tiled_kernel(const __grid_constant__ TiledParams p)
         }
         __syncthreads();
     }
+    TILED_TS(1, 0);
     const TileGeom tg = *reinterpret_cast<const TileGeom*>(s_misc + 4);
     const bool staged = tg.staged == 1;
     const int pitch = p.pitch;          // tile row pitch in cells: fixed per launch, so the walk's tile offsets
@@ -255,8 +270,10 @@ fused_conv_tiled_kernel(const __grid_constant__ TiledParams p)
     const int nrows = store_warp ? 0 : (int)max(0ll, min(32ll, p.total - q0 - r_lo));
     // valid_idx / valid_in_dis_idx rows: elo_count_rows.cuh (skipped when the caller passed NULL for both, e.g. when
     // the stand-alone count kernel of fused_conv_counts.cu writes them concurrently)
-    float* const o_valid = (p.out_valid && nrows > 0) ? p.out_valid + (q0 + r_lo) * kt : nullptr;
-    float* const o_vdis = (p.out_vdis && nrows > 0) ? p.out_vdis + (q0 + r_lo) * kt : nullptr;
+    // (computed where they are used: kept live across the walk they would be spilled, and a reload from local memory
+    // queues behind the stores in flight)
+    auto o_valid = [&]() { return (p.out_valid && nrows > 0) ? p.out_valid + (q0 + r_lo) * kt : nullptr; };
+    auto o_vdis = [&]() { return (p.out_vdis && nrows > 0) ? p.out_vdis + (q0 + r_lo) * kt : nullptr; };
     const bool count_rows = p.out_valid != nullptr || p.out_vdis != nullptr;      // CTA-uniform
     bool early_rows = false;            // CTA-uniform: the store warp writes the count rows while the others walk
 
@@ -293,8 +310,11 @@ fused_conv_tiled_kernel(const __grid_constant__ TiledParams p)
             if (c0 < 0) c0 += g.w2;
             constexpr int SR = 8;
             // empty pixel (reference :98-104); FSETP.GTU there: a NaN pixel counts as a point
+            // An empty pixel is staged as (EMPTY_X, y, z, 1): its squared distance to any centre overflows, so the
+            // select-K walk rejects it by its key alone
             auto put = [&](int r, int c, float x, float y, float z) {
-                t4[r * pitch + c] = make_float4(x, y, z, sq3(x, y, z) <= 1e-10f ? 1.0f : 0.0f);
+                const bool empty = sq3(x, y, z) <= 1e-10f;
+                t4[r * pitch + c] = make_float4(empty ? EMPTY_X : x, y, z, empty ? 1.0f : 0.0f);
                 far = far || !(fmaxf(fmaxf(fabsf(x), fabsf(y)), fabsf(z)) <= p.near_bound);
             };
             if (p.bulk && tg.tw <= g.w2) {
@@ -401,6 +421,7 @@ fused_conv_tiled_kernel(const __grid_constant__ TiledParams p)
         if (far) s_misc[2] = 1;          // some coordinate of the neighbourhood is large, infinite or NaN
         if (!tables_done) fill_tables();
         __syncthreads();
+        TILED_TS(2, 0);
         const bool all_near = SELECT && staged && s_misc[2] == 0;
         early_rows = SW && all_near && count_rows;
         if (store_warp) {
@@ -442,6 +463,7 @@ fused_conv_tiled_kernel(const __grid_constant__ TiledParams p)
                 if (!(p.dbg & 2))
                     write_count_rows(p.out_valid ? p.out_valid + q0 * kt : nullptr, p.out_vdis ? p.out_vdis + q0 * kt : nullptr,
                                      nr, kt, p.vec_ok != 0, p.magic_kt, s_nv, s_ns, lane);
+                TILED_TS(7, TQ);
             }
         } else {
 
@@ -526,11 +548,13 @@ fused_conv_tiled_kernel(const __grid_constant__ TiledParams p)
                         if constexpr (STG) { if (!acc) ++nrej; } else { nsel += acc; }
                     }
                 };
-                // NEAR: an empty pixel gets a key above every threshold, so the key test is the whole filter
+                // NEAR: an empty pixel (staged with x = EMPTY_X) gets a key above every threshold, so the key test is the
+                // whole filter.  The reference's max(d, 1e-10) is left out of the loop: it only matters when two of a
+                // query's candidates are that close, which is caught after the walk and sent to the exact replay.
                 auto eval_near = [&](const float4& c, float& d) {
                     if constexpr (CNT) ninv += c.w;
-                    d = fmaxf(sq3(__fsub_rn(xs, c.x), __fsub_rn(ys, c.y), __fsub_rn(zs, c.z)), 1e-10f);
-                    return __fmaf_rn(c.w, 3e38f, d);
+                    d = sq3(__fsub_rn(xs, c.x), __fsub_rn(ys, c.y), __fsub_rn(zs, c.z));
+                    return d;
                 };
                 for (int jb = 0; jb < kt; jb += QG) {
                     if (jb + QG <= kt) {
@@ -592,6 +616,11 @@ fused_conv_tiled_kernel(const __grid_constant__ TiledParams p)
                 // the K-th place (a cell that fell out of the array could belong between them) goes to the
                 // exact replay.
                 const int nw = min(nsel, K);
+                if constexpr (NEAR) {
+                    // two candidates within the clamp of the reference's max(d, 1e-10): their order there is by scan
+                    // position, not by the unclamped keys of this walk
+                    if (nsel >= 2 && (a[1] & nmask) <= (__float_as_uint(1e-10f) & nmask)) tied = true;
+                }
                 bool prev_eq = false;
                 // cheap screen first: the fix-up below is long straight-line code that most warps never need (two
                 // of a query's K nearest agree in the distance bits of the key in ~1 % of the queries)
@@ -671,6 +700,7 @@ fused_conv_tiled_kernel(const __grid_constant__ TiledParams p)
         s_nv[tid] = 0.f; s_ns[tid] = 0.f; s_nwr[tid] = 0; s_first[tid] = 0; s_bcopy[tid] = b << 1;
     }
     __syncwarp();
+    TILED_TS(3, 0);
 
     // slot `sl` of the warp (row sl / K, slot sl % K) -> (b, hh, ww) and mask
     auto slot_value = [&](unsigned sl, int& vb, int& vh, int& vw, float& vm) {
@@ -716,8 +746,10 @@ fused_conv_tiled_kernel(const __grid_constant__ TiledParams p)
             o_mask[sl] = vm;
         }
     }
+    TILED_TS(4, 0);
     if (!early_rows && !store_warp)
-        write_count_rows(o_valid, o_vdis, nrows, kt, p.vec_ok != 0, p.magic_kt, s_nv + r_lo, s_ns + r_lo, lane);
+        write_count_rows(o_valid(), o_vdis(), nrows, kt, p.vec_ok != 0, p.magic_kt, s_nv + r_lo, s_ns + r_lo, lane);
+    TILED_TS(5, 0);
 
     // ---- exact replay of the tied queries (warp-cooperative, reference scan order), then their rows again ---------
     if (SELECT) {
@@ -767,10 +799,18 @@ fused_conv_tiled_kernel(const __grid_constant__ TiledParams p)
             }
         }
     }
+    TILED_TS(6, 0);
 }
 
+#ifdef ELO_TILED_TS
+extern "C" int elo_debug_tiled_ts(unsigned long long* host, int n)
+{
+    return (int)cudaMemcpyFromSymbol(host, g_tiled_ts, sizeof(unsigned long long) * (size_t)n);
+}
+#endif
+
 static std::atomic<int> g_index_kernel{0};   // 0: by query count, 1: always tiled, 2: always warp-per-query
-static std::atomic<int> g_store_warp_min_kt{getenv("ELO_STORE_WARP_KT") ? atoi(getenv("ELO_STORE_WARP_KT")) : 256};
+static std::atomic<int> g_store_warp_min_kt{getenv("ELO_STORE_WARP_KT") ? atoi(getenv("ELO_STORE_WARP_KT")) : 128};
 // how the tile comes into shared memory: 0 = bulk copies (TMA engine), 1 = plain loads (elo_set_tile_staging)
 static std::atomic<int> g_tile_staging{getenv("ELO_TILE_STAGING") ? atoi(getenv("ELO_TILE_STAGING")) : 0};
 
@@ -892,9 +932,10 @@ int launch_index_tiled(bool select, int B, int H, int W, int N, const Window& g,
     // CTA size: the candidate whose CTAs all fit on the chip at once and load the SMs most evenly
     // CTAs per SM the register budget allows (tiled_min_ctas of the kernel template)
     // A store warp (one more warp per CTA that writes the count rows while the query warps walk) pays for itself
-    // where the walk is long: measured on configs[0]'s frame, 11x41: 171.6 -> 148.7 us; 7x25: 68.3 -> 69.6 us
-    // (the query warps drop from 72 to 64 registers, and stores in flight slow the walk's shared-memory loads even
-    // from another warp); 5x15: 45.3 -> 48.0 us.  elo_set_store_warp_min_cells / ELO_STORE_WARP_KT move the switch-over.
+    // where the walk is long.  Measured on configs[0]'s frame (round 2, final kernels), without -> with: 11x41 139.2 ->
+    // 139.4 us, 7x25 64.1 -> 62.9, 5x15 43.6 -> 43.9 (the query warps drop from 72 to 64 registers, and stores in
+    // flight slow the walk's shared-memory loads even from another warp): used from 128 cells up.
+    // elo_set_store_warp_min_cells / ELO_STORE_WARP_KT move the switch-over.
     const bool sw = select && (out_valid != nullptr || out_vdis != nullptr) &&
                     g.kt >= g_store_warp_min_kt.load(std::memory_order_relaxed);
     auto reg_ctas = [&](int tq) {

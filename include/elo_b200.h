@@ -91,7 +91,7 @@ int elo_get_tile_policy(void);
 int elo_set_index_kernel(int which);
 /* The tile-staged select-K kernel has a form with one extra warp per CTA, the store warp, that writes the CTA's
  * count rows (valid_idx / valid_in_dis_idx) while the query warps walk their windows.  It is used for windows of
- * at least `min_cells` cells (default 256: it wins on 11x41, loses a little on 5x15); 0 = always, a huge value =
+ * at least `min_cells` cells (default 128: it wins on 7x25, loses a little on 5x15); 0 = always, a huge value =
  * never.  Results are identical either way. */
 int elo_set_store_warp_min_cells(int min_cells);
 int elo_get_store_warp_min_cells(void);

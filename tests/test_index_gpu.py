@@ -24,7 +24,7 @@ def index_kernel(request, elo):
     elo._lib.set_tile_staging(1 if request.param == "tiled+plainloads" else 0)
     yield request.param
     elo._lib.set_index_kernel(0)
-    elo._lib.set_store_warp_min_cells(256)
+    elo._lib.set_store_warp_min_cells(128)
     elo._lib.set_tile_staging(0)
 
 
