@@ -4,7 +4,8 @@
 
 UTC*MMA = tcgen05.mma, LDTM / STTM = tcgen05.ld / st, UTCBAR = tcgen05.commit, UBLKCP = cp.async.bulk (TMA bulk
 copy), UTMALDG / UTMASTG = cp.async.bulk.tensor (none: the tiles this path moves are gathers and 12-byte-stride rows,
-which a tensor map cannot describe -- DESIGN.md section 4.1), SYNCS = mbarrier ops, REDUX / VOTE / SHFL = warp
+which a tensor map cannot describe; weights and the index kernel's xyz tile ride the un-tiled UBLKCP -- DESIGN.md
+section 4.1), SYNCS = mbarrier ops, REDUX / VOTE / SHFL = warp
 collectives of the searches."""
 import collections
 import os
