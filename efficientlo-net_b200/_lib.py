@@ -201,6 +201,12 @@ def set_tile_policy(policy):
     check(lib().elo_set_tile_policy(int(policy)), "elo_set_tile_policy")
 
 
+def get_tile_policy():
+    h = lib()
+    h.elo_get_tile_policy.restype = _c_int
+    return int(h.elo_get_tile_policy())
+
+
 def set_pdl(on):
     """Programmatic dependent launch between this library's kernels (default on)."""
     check(lib().elo_set_pdl(int(bool(on))), "elo_set_pdl")

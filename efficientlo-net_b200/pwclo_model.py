@@ -9,6 +9,8 @@ the pose composition into the attention-pooling kernel.  Nothing here synchronis
 whole forward can be captured in a CUDA graph (engine.py).
 """
 import math
+import os
+import threading
 
 import torch
 
@@ -41,6 +43,24 @@ def pyramid_shapes(H_input, W_input):
         oh.append(math.ceil(oh[-1] / STRIDE_H[i]))
         ow.append(math.ceil(ow[-1] / STRIDE_W[i]))
     return oh, ow
+
+
+# Branches of a level on two streams (fork / join): 1 = always, 0 = never, unset = under the latency tile policy only
+# (with several forwards in flight the SMs are busy anyway and the extra graph edges cost more than they give).
+_FORK = os.environ.get("ELO_FORK", "")
+_SIDE = {}
+
+
+def _fork_branches(dev):
+    """(current stream, side stream) when the level's independent chains should run side by side, else None."""
+    if dev.type != "cuda" or _FORK == "0":
+        return None
+    if _FORK != "1" and _lib.get_tile_policy() != 0:
+        return None
+    key = (dev.index, threading.get_ident())
+    if key not in _SIDE:
+        _SIDE[key] = torch.cuda.Stream(device=dev)
+    return torch.cuda.current_stream(dev), _SIDE[key]
 
 
 def _heads(store, lvl):
@@ -266,6 +286,21 @@ def get_model(point_cloud, H_input, W_input, T_gt, T_trans, T_trans_inv, is_trai
                                qrange=qr),
                 pu.search_spec(False, xyz_wp, up_xyz, allq, (7, 15), 8, UP_CONV_DIS[lvl], s_h, s_w, perms[names[1]],
                                qrange=qr)])
+            # The level's two chains after the searches -- cost volume (stage 1 -> stage 2) and the first half of the two
+            # set-upconvs -- do not depend on each other: the set-upconvs go to a side stream (a fork / join that a
+            # captured forward keeps as two branches of the graph), the predictors wait for both.
+            fork = _fork_branches(dev)
+            if fork is not None:
+                main, side = fork
+                searched = torch.cuda.Event()
+                searched.record(main)
+                with torch.cuda.stream(side):
+                    side.wait_event(searched)
+                    ups = pu.up_conv_group(xyz_wp, up_xyz, [up_w, up_pred], (7, 15), s_h, s_w, 8,
+                                           UP_CONV_DIS[lvl], [["%s/up_1_%d" % (n, j) for j in range(2)] for n in names],
+                                           store, [perms[n] for n in names], nbrs=[nu0, nu1], qrange=qr)
+                    joined = torch.cuda.Event()
+                    joined.record(side)
             # cost volume between the warped frame 1 and frame 2 (:242-244)
             cv = pu.cost_volume(xyz_wp, f2(xyz[lvl]), pts_wp, grid(lvl, f2(pts[lvl])), [3, 5], CV_KERNEL_Q[lvl], 4, 6,
                                 COST_VOLUME_DIS[lvl], [128, 64, 64], [128, 64], False, bn_decay,
@@ -273,9 +308,12 @@ def get_model(point_cloud, H_input, W_input, T_gt, T_trans, T_trans_inv, is_trai
                                 random_hw_p=perms["flow_embedding_l%d/p" % lvl], nbr_q=nq_, nbr_p=np_,
                                 qrange1=qr1, qrange2=qr)
             # the two set-upconvs of the level (:247-251) share one launch for their first half ...
-            ups = pu.up_conv_group(xyz_wp, up_xyz, [up_w, up_pred], (7, 15), s_h, s_w, 8,
-                                   UP_CONV_DIS[lvl], [["%s/up_1_%d" % (n, j) for j in range(2)] for n in names],
-                                   store, [perms[n] for n in names], nbrs=[nu0, nu1], qrange=qr)
+            if fork is not None:
+                main.wait_event(joined)
+            else:
+                ups = pu.up_conv_group(xyz_wp, up_xyz, [up_w, up_pred], (7, 15), s_h, s_w, 8,
+                                       UP_CONV_DIS[lvl], [["%s/up_1_%d" % (n, j) for j in range(2)] for n in names],
+                                       store, [perms[n] for n in names], nbrs=[nu0, nu1], qrange=qr)
             # ... and one launch for their second half chained into the two predictors (:253-254)
             rows = B * h * w_
             pts_w = pts_wp.reshape(rows, C)
