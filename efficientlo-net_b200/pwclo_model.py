@@ -163,8 +163,24 @@ def get_model(point_cloud, H_input, W_input, T_gt, T_trans, T_trans_inv, is_trai
         # Samples are stacked frame-major: s = f*B + b reads point_cloud[b, f*N:(f+1)*N, 0:3] in place.
         eye = store.eye(B)
         T_gt = T_gt.to(dev) if T_gt is not None else eye
-        q_gt, t_gt = mu.gt_pose(T_gt, eye if T_trans is None else T_trans.to(dev),
-                                eye if T_trans_inv is None else T_trans_inv.to(dev), aug_frame)
+        # Independent chains run side by side on a second stream under the latency tile policy (_fork_branches): the
+        # ground-truth pose (needed only as an output), pyramid layer 3 beside the initial cost volume, and in every
+        # refinement level the set-upconvs beside the cost volume.
+        fork = _fork_branches(dev)
+        gt_args = (T_gt, eye if T_trans is None else T_trans.to(dev), eye if T_trans_inv is None else T_trans_inv.to(dev),
+                   aug_frame)
+        gt_done = None
+        if fork is not None:
+            main, side = fork
+            started = torch.cuda.Event()
+            started.record(main)
+            with torch.cuda.stream(side):
+                side.wait_event(started)
+                q_gt, t_gt = mu.gt_pose(*gt_args)
+                gt_done = torch.cuda.Event()
+                gt_done.record(side)
+        else:
+            q_gt, t_gt = mu.gt_pose(*gt_args)
         if T_trans is None and aug_frame is None:
             T_aug, T_apply = store.default_aug(B)               # constants: no per-forward tensor ops
         else:
@@ -221,9 +237,21 @@ def get_model(point_cloud, H_input, W_input, T_gt, T_trans, T_trans_inv, is_trai
             scopes = ["sa1/layer%d/conv%d" % (l, j) for j in range(3)]
             rb = band_rows(oh[l + 2], "layer0", ow[l + 2]) if l == 0 else None        # layer 0 (the 64x1800 / 128x2048 image) is banded
             qr = None if rb is None else (rb[0] * ow[l + 2], rb[1] * ow[l + 2])
-            feat = pu.set_conv(src_xyz, src_pts, sel, DOWN_CFG[l][0], DOWN_CFG[l][1], DOWN_CONV_DIS[l], scopes, store,
-                               [perms["sa1/layer%d/f1" % l], perms["sa1/layer%d/f2" % l]], feat_channels=src_c,
-                               set_batch_offsets=(0, B), nbr=nbr_pyr[l], qrange=qr)
+            sa3_done = None
+            if l == 3 and fork is not None:         # layer 3 beside the initial cost volume, joined before level 3's mask
+                fed = torch.cuda.Event()
+                fed.record(main)
+                with torch.cuda.stream(side):
+                    side.wait_event(fed)
+                    feat = pu.set_conv(src_xyz, src_pts, sel, DOWN_CFG[l][0], DOWN_CFG[l][1], DOWN_CONV_DIS[l], scopes,
+                                       store, [perms["sa1/layer%d/f1" % l], perms["sa1/layer%d/f2" % l]],
+                                       feat_channels=src_c, set_batch_offsets=(0, B), nbr=nbr_pyr[l], qrange=qr)
+                    sa3_done = torch.cuda.Event()
+                    sa3_done.record(side)
+            else:
+                feat = pu.set_conv(src_xyz, src_pts, sel, DOWN_CFG[l][0], DOWN_CFG[l][1], DOWN_CONV_DIS[l], scopes, store,
+                                   [perms["sa1/layer%d/f1" % l], perms["sa1/layer%d/f2" % l]], feat_channels=src_c,
+                                   set_batch_offsets=(0, B), nbr=nbr_pyr[l], qrange=qr)
             if rb is not None:
                 band.gather_rows([feat], oh[l + 2], ow[l + 2])
             pts[l] = feat                                                       # (2B, n_l, C_l)
@@ -249,6 +277,8 @@ def get_model(point_cloud, H_input, W_input, T_gt, T_trans, T_trans_inv, is_trai
         _lib.PROFILE_TAG[0] = "l3"
         l3_cv = pu.set_conv(f1(xyz[2]), grid(2, l2_new), sel3, 16, (5, 9), DOWN_CONV_DIS[3],
                             ["new_layer3/conv%d" % j for j in range(3)], store, [perms["new_layer3"]], nbr=nbr_new3)
+        if sa3_done is not None:
+            main.wait_event(sa3_done)
         # ---- level 3: embedding mask, attention pooling, coarse pose (:181-208)
         l3_w = pu.flow_predictor(f1(pts[3]), None, l3_cv, [128, 64], False, bn_decay, "l3_costvolume_predict_ww")
         l3_xyz = f1(xyz[3]).reshape(B, -1, 3)
@@ -289,9 +319,7 @@ def get_model(point_cloud, H_input, W_input, T_gt, T_trans, T_trans_inv, is_trai
             # The level's two chains after the searches -- cost volume (stage 1 -> stage 2) and the first half of the two
             # set-upconvs -- do not depend on each other: the set-upconvs go to a side stream (a fork / join that a
             # captured forward keeps as two branches of the graph), the predictors wait for both.
-            fork = _fork_branches(dev)
             if fork is not None:
-                main, side = fork
                 searched = torch.cuda.Event()
                 searched.record(main)
                 with torch.cuda.stream(side):
@@ -340,6 +368,8 @@ def get_model(point_cloud, H_input, W_input, T_gt, T_trans, T_trans_inv, is_trai
             q_norm[lvl], t_lvl[lvl] = pose["q_norm"], t
             up_xyz, up_w, up_pred = xyz_wp, wgt.view(B, h, w_, 64), pred.view(B, h, w_, 64)
 
+    if gt_done is not None:
+        main.wait_event(gt_done)
     _lib.PROFILE_TAG[0] = ""
     l0_xyz_f1 = f1(xyz[0]).reshape(B, -1, 3)
     return (q_norm[0], t_lvl[0], q_norm[1], t_lvl[1], q_norm[2], t_lvl[2], q_norm[3], t_lvl[3], l0_xyz_f1,
