@@ -1,9 +1,9 @@
 #!/bin/bash
 # On a box with 8 GPUs: the bench line at N = 2, 4, 8 in both multi-GPU modes (frame pairs at 64x1800, row bands of one
-# pair at 128x2048) -> gpurun_out/scale/.  Every run is bounded.
+# pair at 128x2048; BAND_ONLY=1: only the latter) -> gpurun_out/scale/.  Every run is bounded.
 mkdir -p gpurun_out/scale
 for n in ${NS:-2 4 8}; do
-  timeout 240 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29551 \
+  [ -n "${BAND_ONLY:-}" ] || timeout 240 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29551 \
     bench.py --gpus $n --steps 200 --warmup 10 --no-cpu > gpurun_out/scale/pairs_n$n.json 2> gpurun_out/scale/pairs_n$n.err
   timeout 240 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29552 \
     bench.py --gpus $n --partition rowband --hw 128x2048 --steps 50 --warmup 5 > gpurun_out/scale/band128_n$n.json 2> gpurun_out/scale/band128_n$n.err
