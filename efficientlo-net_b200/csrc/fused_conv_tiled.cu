@@ -85,7 +85,7 @@ struct TiledParams {
     int vec_ok;          // every output pointer is 16-byte aligned
     unsigned magic_kt;   // ceil(2^32 / kt), ceil(2^32 / K): exact quotients for the writer's ranges
     unsigned magic_k;
-    int dbg;             // timing aid (ELO_TILED_DBG): 1 = query warps skip the walk, 2 = store warp skips its rows
+    int dbg;             // timing aid (ELO_TILED_DBG): 1 = query warps skip the walk, 2 = store warp skips its rows, 4 = no replay
     int pitch;           // row pitch of the staged tile in cells (TQ + kW)
     float near_bound;    // sqrt(distance^2 / 12.5): coordinates within it are all mutually in range
     int bulk;            // 1: the tile's rows come in by bulk copies (xyz2 is 16-byte aligned); 0: plain loads
@@ -109,9 +109,9 @@ __device__ __forceinline__ int wrap_once(int ww, int w2)
 }
 
 // One insertion into the ascending array a[0..KR): afterwards a holds the KR smallest of (a, x).
-// Branch-free and without a serial chain: a'[i] = min(a[i], max(a[i-1], x)).
+// Branch-free and without a serial chain: a'[i] = min(a[i], max(a[i-1], x)).  Returns the key that fell out.
 template <int KR>
-__device__ __forceinline__ void chain_insert(unsigned (&a)[KR], unsigned x)
+__device__ __forceinline__ unsigned chain_insert(unsigned (&a)[KR], unsigned x)
 {
     unsigned carry = x;
 #pragma unroll
@@ -120,6 +120,7 @@ __device__ __forceinline__ void chain_insert(unsigned (&a)[KR], unsigned x)
         a[i] = min(a[i], carry);
         carry = m;
     }
+    return carry;
 }
 
 // Threads per CTA: TQ query threads; a select-K CTA has one more warp, the STORE WARP.  The counts of a select-K
@@ -529,6 +530,8 @@ fused_conv_tiled_kernel(const __grid_constant__ TiledParams p)
                 for (int i = 0; i < KR; ++i) a[i] = KEY_NONE;
                 const unsigned jmask = (1u << p.jbits) - 1u, nmask = ~jmask;     // jbits >= 4: QG positions fit
                 unsigned thr = NEAR ? (KEY_NONE | jmask) : 0xffffffffu;
+                unsigned ev = 0xffffffffu;      // smallest key that ever fell out of the array (a cell the filter turned
+                                                // away had larger distance bits than the last key of its time)
                 const unsigned qbase = (unsigned)__cvta_generic_to_shared(queue + tid);
                 unsigned qp = qbase;
                 // centre of a query that must accept nothing (NEAR path): every distance overflows
@@ -596,7 +599,7 @@ fused_conv_tiled_kernel(const __grid_constant__ TiledParams p)
                     const int n = __reduce_max_sync(FULL_MASK, cnt);
                     for (int t = 0; t < n; ++t) {
                         const unsigned x = t < cnt ? (queue[t * TQ + tid] | (unsigned)jb) : 0xffffffffu;
-                        chain_insert<KR>(a, x);
+                        ev = min(ev, chain_insert<KR>(a, x));
                     }
                     qp = qbase;
                     thr = a[KR - 1] | jmask;
@@ -611,10 +614,9 @@ fused_conv_tiled_kernel(const __grid_constant__ TiledParams p)
                 }
                 if constexpr (STG && !NEAR) { nsel = kt - nrej; nvalid = kt - (int)ninv; }
                 if (!cvalid) { nsel = 0; nvalid = 0; }
-                // Near-ties: adjacent keys whose distance bits agree.  An isolated pair inside the K nearest is
-                // put in order by its exact distances; an exact tie, a run of three, or a pair that straddles
-                // the K-th place (a cell that fell out of the array could belong between them) goes to the
-                // exact replay.
+                // Near-ties: adjacent keys whose distance bits agree.  An isolated pair -- inside the K nearest or
+                // across the K-th place -- is put in order by its exact distances; an exact tie or a run of three
+                // (counting the smallest key that fell out of the array) goes to the exact replay.
                 const int nw = min(nsel, K);
                 if constexpr (NEAR) {
                     // two candidates within the clamp of the reference's max(d, 1e-10): their order there is by scan
@@ -633,7 +635,11 @@ fused_conv_tiled_kernel(const __grid_constant__ TiledParams p)
                 for (int i = 0; i + 1 < KR; ++i) {
                     const bool eq = i < K && i + 1 < nsel && ((a[i] ^ a[i + 1]) & nmask) == 0u;
                     if (eq) {
-                        if (prev_eq || i + 1 >= K) {
+                        // a pair that straddles the K-th place can be settled by its exact distances unless the next
+                        // key -- in the array, or the smallest that fell out of it -- agrees with it in the distance bits
+                        // too (that cell could belong between them)
+                        const unsigned nxt = (i + 2 < KR) ? a[i + 2 < KR ? i + 2 : KR - 1] : ev;
+                        if (prev_eq || (i + 1 >= K && ((nxt ^ a[i + 1]) & nmask) == 0u)) {
                             tied = true;
                         } else {
                             const float d0 = exact_d((int)(a[i] & jmask)), d1 = exact_d((int)(a[i + 1] & jmask));
@@ -754,7 +760,7 @@ fused_conv_tiled_kernel(const __grid_constant__ TiledParams p)
     // ---- exact replay of the tied queries (warp-cooperative, reference scan order), then their rows again ---------
     if (SELECT) {
         __syncthreads();                        // every walk is over: tie list complete, tile free
-        const int nties = s_misc[0];
+        const int nties = (p.dbg & 4) ? 0 : s_misc[0];       // dbg 4: no replay (timing aid; tied queries stay approximate)
         if (nties > 0) {
             int2* off_scan = reinterpret_cast<int2*>(tile);
             float* dist = reinterpret_cast<float*>(tile + (size_t)kt * 8) + (size_t)warp * kt;
