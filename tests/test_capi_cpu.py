@@ -52,3 +52,27 @@ def test_product_never_imports_the_oracle():
             text = open(path).read()
             assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), path
             assert "libelo_oracle" not in text and "oracle/_ref" not in text, path
+
+
+def test_zero_widened_chain_computes_the_same_function(elo):
+    """packing.folded_chain(pad_hidden=64): the 32-32-64 set-conv of pyramid layer 2 runs on the 64-/128-wide GEMM engines
+    with its hidden layers widened by zero columns (zero bias) and the next layer by matching zero rows -- the chain of
+    ReLU(x W + b) layers must give the same outputs, bit for bit where the added terms are exact zeros."""
+    import torch
+    P = elo.params.init_params(0)
+    scopes = ["sa1/layer2/conv%d" % j for j in range(3)]
+    plain = elo.packing.folded_chain(P, scopes)
+    wide = elo.packing.folded_chain(P, scopes, pad_hidden=64)
+    assert [tuple(w.shape) for w, _ in plain] == [(35, 32), (32, 32), (32, 64)]
+    assert [tuple(w.shape) for w, _ in wide] == [(35, 64), (64, 64), (64, 64)]
+    x = torch.randn(257, 35, generator=torch.Generator().manual_seed(0))
+
+    def run(chain):
+        y = x.double()
+        for w, b in chain:
+            y = torch.relu(y @ w.double() + b.double())
+        return y
+
+    assert torch.equal(run(plain), run(wide)[:, :64])
+    # the widened stream is what the engines take: 64-wide layers only
+    assert elo.packing.pack_stream(P, scopes, pad_hidden=64).numel() % 64 == 0
