@@ -23,6 +23,8 @@
 
 namespace elo {
 
+constexpr int PROJECT_CTAS_THROUGHPUT = 2;    // CTAs per SM of the projection passes under the throughput tile policy
+
 struct ProjParams {
     int B, N, H, W, C, mode;
     const float* points; long long point_stride, batch_stride, outer_stride; int inner_batch;
@@ -532,9 +534,14 @@ extern "C" int elo_project(const elo_project_desc* d, void* stream)
     p.keys = reinterpret_cast<int2*>(d->point_keys);
     cudaStream_t st = (cudaStream_t)stream;
     const int sms = device_info().sm_count;
+    // CTAs per SM: 8 x 256 threads fill an SM's thread slots -- the shortest kernel, but both passes wait on memory
+    // (atomics, scattered loads) most of the time.  Under the throughput tile policy fewer CTAs with more points per
+    // thread leave the slots to the other forwards in flight (ELO_PROJECT_CAP overrides).
+    static const int cap_env = getenv("ELO_PROJECT_CAP") ? atoi(getenv("ELO_PROJECT_CAP")) : 0;
+    const int per_sm = cap_env > 0 ? cap_env : (elo_get_tile_policy() == 1 ? PROJECT_CTAS_THROUGHPUT : 8);
     auto blocks = [&](long long work) {
         long long b = (work + 255) / 256;
-        const long long cap = (long long)sms * 8;
+        const long long cap = (long long)sms * per_sm;
         return (unsigned)(b < 1 ? 1 : (b > cap ? cap : b));
     };
     const long long cells = (long long)p.B * p.H * p.W;
